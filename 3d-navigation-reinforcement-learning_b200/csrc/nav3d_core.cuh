@@ -1,0 +1,443 @@
+// nav3d_core.cuh — per-environment logic of the batched CubicEnv step, written once and instantiated for a group of
+// G cooperating lanes (G = 1 .. 32).  Everything here is device code for sm_100a; the functions are also marked
+// __host__ so that tests/emu can run the SAME source with G = 1 on the CPU as a debugging aid (never shipped,
+// never on the product path).
+//
+// Reference being replaced (semantics, not structure): envs/CubicEnv.py of Noimps/3D-Navigation-Reinforcement-Learning
+//   step :110-132, do_action :134-166, compute_reward :169-224, _get_3d_local_map :229-251, get_obs :254-312,
+//   _mark_visited :322-343, _sense_direction :345-397, reset :77-108, load_room's start pick :450-462.
+//
+// Data model.  The reference keeps one int64 per voxel per env (internal_grid: -2 known wall, -1 unknown,
+// 0 seen, >=1 visit counter).  Here that grid is factored into
+//   * the static room occupancy, shared by all envs, bit-packed in three orientations so that each of the six
+//     axis-aligned rays is ONE 64-bit word + a bit scan (no per-cell march):
+//        occz[x][y] : u16, bit z        occx[y][z] : u64, bit x        occy[x][z] : u64, bit y
+//   * a per-env "seen" bit volume S: u16 per (x,y) column (bit z), stored in 4x4-column tiles of 32 B (one sector)
+//   * a per-env visit-count volume C: u8 per cell, saturating at 255, stored in 4x4x2 bricks of 32 B
+//   internal_grid[c] == (!S[c] ? -1 : occ[c] ? -2 : C[c]).  Observations clip counters at 20 and the reward at 25
+//   (CubicEnv.py:273-274, :180), so saturation at 255 changes no output.
+// No lane ever depends on another lane's memory writes inside a step (the window gather re-derives the freshly seen
+// bits from the ray extents in registers), so a step needs no intra-group synchronisation; only a reset does.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define NAV3D_HD __host__ __device__ __forceinline__
+
+namespace nav3d {
+
+constexpr int kObsDim = 80;
+constexpr uint32_t kStreamReset = 0x52455345u;   // include/nav3d.h "Random streams"
+constexpr uint32_t kStreamAction = 0x41435449u;
+
+// flag bits of EnvState::flags
+constexpr uint32_t kNearWall = 1u, kWasNearWall = 2u, kLastBump = 4u, kDone = 8u;
+
+struct alignas(32) RoomDev {       // one per room, read-only after nav3d_load_rooms
+    uint16_t W, D, H, ntx;         // dims; ntx = ceil(W/4) tiles along x
+    uint16_t nty, nbz;             // nty = ceil(D/4); nbz = ceil(H/2) bricks along z
+    uint32_t n_free;               // total_free_cells == max_steps (CubicEnv.py:450-459)
+    uint32_t occz_off;             // u16 index into occz pool, [x][y]
+    uint32_t occx_off;             // u64 index into occ64 pool, [y][z], bit x
+    uint32_t occy_off;             // u64 index into occ64 pool, [x][z], bit y
+    uint32_t free_off;             // u32 index into the free-cell pool (x | y<<8 | z<<16, reference scan order)
+};
+static_assert(sizeof(RoomDev) == 32, "RoomDev must be one 32-byte sector");
+
+struct alignas(32) EnvState {      // one 32-byte sector per env: read once, written once per step
+    uint8_t x, y, z, facing;
+    uint8_t last_action, flags, down, pad0;
+    uint32_t step_count, visited_count, bump_count;
+    int32_t ret_centi;             // running episode return in 1/100 units, crash penalties excluded
+    uint32_t episode;              // number of resets so far == index into the Philox reset stream
+    uint16_t room, pad1;
+};
+static_assert(sizeof(EnvState) == 32, "EnvState must be one 32-byte sector");
+
+struct EngineParams {
+    const RoomDev *rooms;
+    const uint16_t *occz;
+    const unsigned long long *occ64;
+    const uint32_t *free_cells;
+    EnvState *states;
+    uint8_t *know;                 // per-env knowledge storage: [S tiles | C bricks]
+    unsigned long long env_stride; // bytes per env in `know`
+    uint32_t c_off;                // byte offset of the C bricks inside an env block
+    int32_t n_envs, n_rooms, L;
+    uint32_t env_id0, seed_lo, seed_hi;
+    int32_t auto_reset;
+    double crash_penalty;
+};
+
+struct StepIO {                    // per-launch output pointers (any may be null except obs)
+    const long long *actions;
+    float *obs;
+    float *reward;
+    double *reward64;
+    uint8_t *terminated, *truncated;
+    float *terminal_obs;
+    void *episodes;                // nav3d_episode*
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+NAV3D_HD int ffs64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)v);
+#else
+    return v ? __builtin_ctzll(v) + 1 : 0;
+#endif
+}
+NAV3D_HD int clz64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return __clzll((long long)v);
+#else
+    return v ? __builtin_clzll(v) : 64;
+#endif
+}
+NAV3D_HD float fdiv_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+template <typename T> NAV3D_HD T ldg(const T *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+NAV3D_HD int imin(int a, int b) { return a < b ? a : b; }
+
+template <int G> NAV3D_HD void group_sync(int lane_in_warp) {
+#ifdef __CUDA_ARCH__
+    if (G == 32) __syncwarp();
+    else if (G > 1) {
+        unsigned m = (G >= 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane_in_warp & ~(G - 1));
+        __syncwarp(m);
+    }
+#else
+    (void)lane_in_warp;
+#endif
+}
+
+// Philox4x32-10 (Salmon et al., SC'11)
+NAV3D_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                            uint32_t &o0, uint32_t &o1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1;
+}
+NAV3D_HD uint32_t mulhi_range(uint32_t u, uint32_t n) { return (uint32_t)(((unsigned long long)u * n) >> 32); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// knowledge-storage addressing
+// ---------------------------------------------------------------------------------------------------------------
+NAV3D_HD uint32_t s_index(const RoomDev &R, int x, int y) {          // u16 index of column (x,y) in the S tiles
+    return (uint32_t)((((y >> 2) * R.ntx + (x >> 2)) << 4) + ((x & 3) << 2) + (y & 3));
+}
+NAV3D_HD uint32_t c_index(const RoomDev &R, int x, int y, int z) {   // byte index of cell (x,y,z) in the C bricks
+    return (uint32_t)(((((y >> 2) * R.ntx + (x >> 2)) * R.nbz + (z >> 1)) << 5) + ((x & 3) << 3) + ((y & 3) << 1) + (z & 1));
+}
+NAV3D_HD uint32_t s_bytes(const RoomDev &R) { return (uint32_t)R.ntx * R.nty * 32u; }
+NAV3D_HD uint32_t c_bytes(const RoomDev &R) { return (uint32_t)R.ntx * R.nty * R.nbz * 32u; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// rays: _sense_direction (CubicEnv.py:345-397) for all six directions at once, from the packed occupancy
+// ---------------------------------------------------------------------------------------------------------------
+struct Rays {
+    int x0, x1, y0, y1;        // inclusive extents of the cells whose knowledge the +-x / +-y rays touch
+    uint32_t zmask;            // bits of the centre column touched by the +-z rays (centre bit included)
+    int near_wall;             // a wall at distance 1 in any direction (:378-379)
+    int down;                  // free cells seen below (:394-395)
+};
+
+// cells p+1 .. p+n along increasing bit index of w
+NAV3D_HD void ray_up(unsigned long long w, int p, int n, int &ext, int &nfree, int &near) {
+    ext = 0; nfree = 0; near = 0;
+    if (n <= 0) return;
+    unsigned long long m = w >> (p + 1);                 // n > 0 implies p + 1 <= 63
+    int f = ffs64(m);                                    // 1-based distance of the first wall, 0 = none
+    if (f != 0 && f <= n) { ext = f; nfree = f - 1; near = (f == 1); }
+    else { ext = n; nfree = n; }
+}
+// cells p-1 .. p-n along decreasing bit index of w
+NAV3D_HD void ray_down(unsigned long long w, int p, int n, int &ext, int &nfree, int &near) {
+    ext = 0; nfree = 0; near = 0;
+    if (n <= 0) return;                                  // n > 0 implies 1 <= p <= 63
+    unsigned long long m = w << (64 - p);                // bit 63 = cell p-1
+    int f = m ? clz64(m) + 1 : 0;
+    if (f != 0 && f <= n) { ext = f; nfree = f - 1; near = (f == 1); }
+    else { ext = n; nfree = n; }
+}
+
+NAV3D_HD Rays cast_rays(const EngineParams &P, const RoomDev &R, int x, int y, int z) {
+    const int L = P.L, W = R.W, D = R.D, H = R.H;
+    unsigned long long wx = ldg(P.occ64 + R.occx_off + (uint32_t)(y * H + z));
+    unsigned long long wy = ldg(P.occ64 + R.occy_off + (uint32_t)(x * H + z));
+    unsigned long long wz = ldg(P.occz + R.occz_off + (uint32_t)(x * D + y));
+    Rays r;
+    int ext, nfree, near, any = 0;
+    ray_up(wx, x, imin(L, W - 1 - x), ext, nfree, near);   r.x1 = x + ext; any |= near;
+    ray_down(wx, x, imin(L, x), ext, nfree, near);         r.x0 = x - ext; any |= near;
+    ray_up(wy, y, imin(L, D - 1 - y), ext, nfree, near);   r.y1 = y + ext; any |= near;
+    ray_down(wy, y, imin(L, y), ext, nfree, near);         r.y0 = y - ext; any |= near;
+    int zu, zd;
+    ray_up(wz, z, imin(L, H - 1 - z), zu, nfree, near);    any |= near;
+    ray_down(wz, z, imin(L, z), zd, nfree, near);          any |= near;
+    r.down = nfree;
+    r.zmask = ((2u << (z + zu)) - 1u) & ~((1u << (z - zd)) - 1u);
+    r.near_wall = any;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// get_obs (CubicEnv.py:254-312): fold the rays into S, gather the 4x4x4 window, write the 80 floats
+// ---------------------------------------------------------------------------------------------------------------
+struct ObsScalars {
+    int facing, last_action, was_near_wall, last_bump, down;
+    uint32_t visited, total_free;
+};
+
+template <int G>
+NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z,
+                      const Rays &r, int centre_count, bool write_seen, const ObsScalars &sc, const float *lut,
+                      float *obs_row) {
+    uint16_t *S = reinterpret_cast<uint16_t *>(envk);
+    const uint8_t *C = envk + P.c_off;
+    const uint32_t zbit = 1u << z;
+
+    // Step 1 (:264-266): mark every cell the six rays examined as seen.
+    if (write_seen) {
+        const int nx = r.x1 - r.x0 + 1, ny = r.y1 - r.y0 + 1;
+        for (int i = lane; i < nx + ny; i += G) {
+            int cx, cy;
+            if (i < nx) { cx = r.x0 + i; cy = y; }
+            else { cx = x; cy = r.y0 + (i - nx); if (cy == y) continue; }     // centre column belongs to the x run
+            uint32_t m = (cx == x && cy == y) ? r.zmask : zbit;
+            uint16_t *p = S + s_index(R, cx, cy);
+            uint32_t o = *p, n = o | m;
+            if (n != o) *p = (uint16_t)n;
+        }
+    }
+    if (obs_row == nullptr) return;
+
+    // Step 2 (:270-275) + Steps 3-6: 16 window columns + 4 scalar quads = 20 float4 stores per env.
+    for (int j = lane; j < 20; j += G) {
+        float4 v;
+        if (j < 16) {
+            const int cx = x + (j >> 2) - 2, cy = y + (j & 3) - 2;
+            const float unknown = lut[1];
+            v.x = v.y = v.z = v.w = unknown;
+            if (cx >= 0 && cx < R.W && cy >= 0 && cy < R.D) {
+                uint32_t sw = S[s_index(R, cx, cy)];
+                if (cy == y && cx >= r.x0 && cx <= r.x1) sw |= (cx == x) ? r.zmask : zbit;
+                if (cx == x && cy >= r.y0 && cy <= r.y1) sw |= zbit;
+                const uint32_t ow = ldg(P.occz + R.occz_off + (uint32_t)(cx * R.D + cy));
+                float out[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int cz = z - 2 + k;
+                    float f = unknown;
+                    if (cz >= 0 && cz < R.H && ((sw >> cz) & 1u)) {
+                        if ((ow >> cz) & 1u) f = lut[0];                      // known wall: (-2+2)/22
+                        else {
+                            int c = (cx == x && cy == y && cz == z) ? centre_count : (int)C[c_index(R, cx, cy, cz)];
+                            f = lut[2 + imin(c, 20)];
+                        }
+                    }
+                    out[k] = f;
+                }
+                v.x = out[0]; v.y = out[1]; v.z = out[2]; v.w = out[3];
+            }
+        } else if (j == 16) {
+            v.x = sc.facing == 0 ? 1.f : 0.f; v.y = sc.facing == 1 ? 1.f : 0.f;
+            v.z = sc.facing == 2 ? 1.f : 0.f; v.w = sc.facing == 3 ? 1.f : 0.f;
+        } else if (j == 17) {
+            // float(k)/5, count/L and visited/total are f64 quotients rounded to f32 in the reference (:284-291); for
+            // integers below 2^24 that equals the correctly rounded f32 quotient (53 >= 2*24+2, Figueroa 1995).
+            v.x = fdiv_rn((float)sc.last_action, 5.0f);
+            v.y = (float)sc.was_near_wall;
+            v.z = (float)sc.last_bump;
+            v.w = fdiv_rn((float)sc.down, (float)P.L);
+        } else if (j == 18) {
+            v.x = fdiv_rn((float)sc.visited, (float)sc.total_free);
+            v.y = v.z = v.w = 0.f;
+        } else {
+            v.x = v.y = v.z = v.w = 0.f;
+        }
+        reinterpret_cast<float4 *>(obs_row)[j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reset (CubicEnv.py:77-108) of one env, room/start already chosen
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+NAV3D_HD void reset_env(const EngineParams &P, int env, int lane, int lane_in_warp, uint32_t room_idx, uint32_t k,
+                        uint32_t episode_after, const float *lut, float *obs_row) {
+    const RoomDev R = P.rooms[room_idx];
+    uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
+    // internal_grid = full(-1) (:84): nothing seen, nothing counted
+    {
+        uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *s4 = reinterpret_cast<uint4 *>(envk);
+        const uint32_t ns = s_bytes(R) >> 4;
+        for (uint32_t i = lane; i < ns; i += G) s4[i] = zero;
+        uint4 *c4 = reinterpret_cast<uint4 *>(envk + P.c_off);
+        const uint32_t nc = c_bytes(R) >> 4;
+        for (uint32_t i = lane; i < nc; i += G) c4[i] = zero;
+    }
+    group_sync<G>(lane_in_warp);
+    const uint32_t cell = ldg(P.free_cells + R.free_off + k);
+    const int x = cell & 0xff, y = (cell >> 8) & 0xff, z = (cell >> 16) & 0xff;
+    if (lane == 0) envk[P.c_off + c_index(R, x, y, z)] = 1;           // internal_grid[start] = 1 (:85)
+    const Rays r = cast_rays(P, R, x, y, z);                          // get_obs() inside reset (:108)
+    ObsScalars sc;
+    sc.facing = 0; sc.last_action = 0; sc.was_near_wall = 0; sc.last_bump = 0; sc.down = r.down;
+    sc.visited = 1; sc.total_free = R.n_free;
+    observe<G>(P, R, envk, lane, x, y, z, r, 1, true, sc, lut, obs_row);
+    if (lane == 0) {
+        EnvState st;
+        st.x = (uint8_t)x; st.y = (uint8_t)y; st.z = (uint8_t)z; st.facing = 0;
+        st.last_action = 0; st.flags = (uint8_t)(r.near_wall ? kNearWall : 0u); st.down = (uint8_t)r.down; st.pad0 = 0;
+        st.step_count = 0; st.visited_count = 1; st.bump_count = 0; st.ret_centi = 0;
+        st.episode = episode_after; st.room = (uint16_t)room_idx; st.pad1 = 0;
+        P.states[env] = st;
+    }
+}
+
+template <int G>
+NAV3D_HD void reset_env_philox(const EngineParams &P, int env, int lane, int lane_in_warp, uint32_t episode,
+                               const float *lut, float *obs_row) {
+    uint32_t u0, u1;
+    philox4x32_10(P.env_id0 + (uint32_t)env, episode, 0u, kStreamReset, P.seed_lo, P.seed_hi, u0, u1);
+    const uint32_t room = mulhi_range(u0, (uint32_t)P.n_rooms);       // random.choice(self.rooms) (:407)
+    const uint32_t nf = ldg(&P.rooms[room].n_free);
+    const uint32_t k = mulhi_range(u1, nf);                           // random.choice(possible_start_pose) (:462)
+    reset_env<G>(P, env, lane, lane_in_warp, room, k, episode + 1u, lut, obs_row);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// step (CubicEnv.py:110-132) of one env
+// ---------------------------------------------------------------------------------------------------------------
+struct EpisodeRec { float episode_return; int32_t length, bumps, visited, total_free, room, terminated, truncated; };
+
+template <int G>
+NAV3D_HD void step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
+                       const float *lut, long long row /* row index for the output arrays */) {
+    const EnvState st = P.states[env];
+    const RoomDev R = P.rooms[st.room];
+    uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
+    uint8_t *C = envk + P.c_off;
+
+    int a = action < 0 ? 0 : (action > 5 ? 5 : action);
+    uint32_t flags = st.flags;
+    if (flags & kNearWall) flags = (flags | kWasNearWall) & ~kNearWall;          // :111-113
+    const uint32_t step_count = st.step_count + 1u;                              // :115
+    const bool truncated = step_count >= R.n_free;                               // :116, max_steps = total_free (:459)
+
+    // do_action (:134-166)
+    int x = st.x, y = st.y, z = st.z, facing = st.facing;
+    int tx = x, ty = y, tz = z;
+    if (a < 4) {
+        facing = (facing + a) & 3;                                               // table :135-140 == rotate by a; :148-151
+        tx += (facing == 1) - (facing == 3);
+        ty += (facing == 0) - (facing == 2);
+    } else tz += (a == 4) ? 1 : -1;
+    bool moved = false;
+    if (tx >= 0 && tx < R.W && ty >= 0 && ty < R.D && tz >= 0 && tz < R.H) {     // _mark_visited :328-332
+        const uint32_t ow = ldg(P.occz + R.occz_off + (uint32_t)(tx * R.D + ty));
+        moved = !((ow >> tz) & 1u);
+    }
+    if (moved) { x = tx; y = ty; z = tz; }
+    const uint32_t cidx = c_index(R, x, y, z);
+    const int c_old = C[cidx];
+    // entering: 0 -> 1 (+visited, explored) or v -> v+1 (:335-341); then the unconditional += 1 at the final
+    // position (:165-166).  A bump only gets the latter.
+    const bool explored = moved && c_old == 0;
+    const int c_new = imin(255, c_old + (moved ? 2 : 1));
+    if (lane == 0) C[cidx] = (uint8_t)c_new;
+    const uint32_t visited = st.visited_count + (explored ? 1u : 0u);
+    const bool bumped = !moved;
+
+    // termination test of compute_reward (:212-214): visited/total >= 0.84 in f64.  For total <= 65536 this is
+    // exactly 25*visited >= 21*total (tests/test_host_logic.py::test_finish_threshold_integer_form).
+    const bool done = (25ull * visited >= 21ull * R.n_free) ;
+    const bool will_reset = P.auto_reset && (done || truncated);
+
+    // get_obs (:122)
+    Rays r;
+    float *orow = io.obs + row * kObsDim;
+    if (will_reset) orow = io.terminal_obs ? io.terminal_obs + row * kObsDim : nullptr;
+    const bool need_obs = !will_reset || orow != nullptr;
+    if (need_obs) {
+        r = cast_rays(P, R, x, y, z);
+        ObsScalars sc;
+        sc.facing = facing; sc.last_action = st.last_action; sc.was_near_wall = (flags & kWasNearWall) != 0;
+        sc.last_bump = (flags & kLastBump) != 0; sc.down = r.down; sc.visited = visited; sc.total_free = R.n_free;
+        observe<G>(P, R, envk, lane, x, y, z, r, c_new, !will_reset, sc, lut, orow);
+        if (r.near_wall) flags |= kNearWall;
+    } else { r.down = 0; }
+
+    if (lane == 0) {
+        // compute_reward (:169-224), same operations in the same order, f64
+        double rew = -0.05;
+        const double pen = (double)c_new * 0.02;
+        rew -= (pen < 0.5) ? pen : 0.5;
+        int cents = -5 - imin(2 * c_new, 50);
+        uint32_t bump_count = st.bump_count;
+        if (bumped) {
+            flags |= kLastBump; bump_count++;
+            rew += P.crash_penalty;
+        } else {
+            flags &= ~kLastBump;
+            if (flags & kWasNearWall) { flags &= ~kWasNearWall; rew += 0.15; cents += 15; }
+            if (st.last_action != 2 && a == st.last_action && st.last_action < 4) { rew += 0.05; cents += 5; }
+            if (st.last_action == 2 && a == 2) { rew -= 0.5; cents -= 50; }
+        }
+        if (explored) { rew += 1.0; cents += 100; }
+        if (done) { flags |= kDone; rew += 100.0; cents += 10000; }
+        if (truncated) { rew += -5.0; cents -= 500; }
+        const int ret_centi = st.ret_centi + cents;
+
+        io.reward[row] = (float)rew;
+        if (io.reward64) io.reward64[row] = rew;
+        io.terminated[row] = done ? 1 : 0;
+        io.truncated[row] = truncated ? 1 : 0;
+        if ((done || truncated) && io.episodes) {
+            EpisodeRec ep;
+            ep.episode_return = (float)((double)ret_centi / 100.0 + (double)bump_count * P.crash_penalty);
+            ep.length = (int32_t)step_count; ep.bumps = (int32_t)bump_count; ep.visited = (int32_t)visited;
+            ep.total_free = (int32_t)R.n_free; ep.room = st.room; ep.terminated = done; ep.truncated = truncated;
+            reinterpret_cast<EpisodeRec *>(io.episodes)[row] = ep;
+        }
+        if (!will_reset) {
+            EnvState ns;
+            ns.x = (uint8_t)x; ns.y = (uint8_t)y; ns.z = (uint8_t)z; ns.facing = (uint8_t)facing;
+            ns.last_action = (uint8_t)a; ns.flags = (uint8_t)flags; ns.down = (uint8_t)r.down; ns.pad0 = 0;
+            ns.step_count = step_count; ns.visited_count = visited; ns.bump_count = bump_count;
+            ns.ret_centi = ret_centi; ns.episode = st.episode; ns.room = st.room; ns.pad1 = 0;
+            P.states[env] = ns;
+        }
+    }
+    if (will_reset) {
+        // every lane's reads of the old knowledge are done before any lane clears it
+        group_sync<G>(lane_in_warp);
+        reset_env_philox<G>(P, env, lane, lane_in_warp, st.episode, lut, io.obs + row * kObsDim);
+    }
+}
+
+}  // namespace nav3d

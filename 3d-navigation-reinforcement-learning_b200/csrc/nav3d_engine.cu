@@ -1,0 +1,579 @@
+// nav3d_engine.cu — kernels and C ABI of libnav3d_b200.so (see include/nav3d.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see __graft_entry__.build).
+// CUDA runtime only: no torch types, no CPU fallback.
+#include "nav3d_core.cuh"
+#include "../../include/nav3d.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace nav3d;
+
+static_assert(sizeof(EpisodeRec) == sizeof(nav3d_episode), "episode record layout");
+static_assert(kObsDim == NAV3D_OBS_DIM, "obs dim");
+
+namespace {
+
+constexpr int kBlock = 128;   // threads per CTA for the per-env kernels
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(NAV3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+
+__device__ __forceinline__ void fill_lut(float *lut) {
+    // (m + 2) / 22 in f32 for m = -2 .. 20 (CubicEnv.py:273-275), correctly rounded like NumPy's f32 divide
+    if (threadIdx.x < 23) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 22.0f);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// load_room's grid -> packed room (CubicEnv.py:421-459).  One CTA per room.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_rooms_kernel(const int8_t *__restrict__ dense,
+                                                         const uint32_t *__restrict__ dense_off,
+                                                         const int32_t *__restrict__ wall_code, RoomDev *rooms,
+                                                         uint16_t *occz, unsigned long long *occ64, uint32_t *free_cells,
+                                                         uint32_t *n_wall) {
+    __shared__ uint32_t cnt[NAV3D_MAX_WIDTH * NAV3D_MAX_DEPTH + 1];
+    __shared__ uint32_t walls;
+    const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const RoomDev R = rooms[r];
+    const int W = R.W, D = R.D, H = R.H;
+    const int8_t *g = dense + dense_off[r];
+    const int wc = wall_code[r];
+    if (tid == 0) walls = 0;
+    __syncthreads();
+    // column words: occz[x][y], bit z
+    const uint32_t zin = H >= 3 ? (((1u << (H - 1)) - 1u) & ~1u) : 0u;   // interior layers 1..H-2
+    for (int c = tid; c < W * D; c += nt) {
+        const int x = c / D, y = c - x * D;
+        uint32_t bits = 0;
+        for (int z = 0; z < H; z++) bits |= (g[(size_t)c * H + z] == wc ? 1u : 0u) << z;
+        occz[R.occz_off + c] = (uint16_t)bits;
+        const bool interior = x >= 1 && x <= W - 2 && y >= 1 && y <= D - 2;
+        cnt[c] = interior ? __popc(~bits & zin) : 0u;
+        atomicAdd(&walls, (uint32_t)__popc(bits));
+    }
+    // row words along x: occx[y][z], bit x
+    for (int c = tid; c < D * H; c += nt) {
+        const int y = c / H, z = c - y * H;
+        unsigned long long bits = 0;
+        for (int x = 0; x < W; x++) bits |= (unsigned long long)(g[((size_t)x * D + y) * H + z] == wc) << x;
+        occ64[R.occx_off + c] = bits;
+    }
+    // row words along y: occy[x][z], bit y
+    for (int c = tid; c < W * H; c += nt) {
+        const int x = c / H, z = c - x * H;
+        unsigned long long bits = 0;
+        for (int y = 0; y < D; y++) bits |= (unsigned long long)(g[((size_t)x * D + y) * H + z] == wc) << y;
+        occ64[R.occy_off + c] = bits;
+    }
+    __syncthreads();
+    // exclusive scan of the per-column free counts in (x, y) order: possible_start_pose order (:450-457)
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int c = 0; c < W * D; c++) { uint32_t v = cnt[c]; cnt[c] = run; run += v; }
+        cnt[W * D] = run;
+        rooms[r].n_free = run;
+        n_wall[r] = walls;
+    }
+    __syncthreads();
+    for (int c = tid; c < W * D; c += nt) {
+        const int x = c / D, y = c - x * D;
+        const bool interior = x >= 1 && x <= W - 2 && y >= 1 && y <= D - 2;
+        if (!interior) continue;
+        uint32_t freebits = ~(uint32_t)occz[R.occz_off + c] & zin;
+        uint32_t o = R.free_off + cnt[c];
+        while (freebits) {
+            const int z = __ffs(freebits) - 1;
+            freebits &= freebits - 1;
+            free_cells[o++] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)z << 16);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-env kernels: G lanes per env, kBlock / G envs per CTA
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kBlock) reset_kernel(EngineParams P, const int32_t *__restrict__ env_ids, int n,
+                                                       const int32_t *__restrict__ picks, float *obs) {
+    __shared__ float lut[24];
+    fill_lut(lut);
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long idx = gid / G;
+    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
+    if (idx >= n) return;
+    const int env = env_ids ? env_ids[idx] : (int)idx;
+    if (env < 0 || env >= P.n_envs) return;
+    float *orow = obs ? obs + (long long)env * kObsDim : nullptr;
+    const uint32_t episode = P.states[env].episode;
+    group_sync<G>(liw);   // every lane has read the episode counter before lane 0 rewrites the state
+    if (picks) {
+        uint32_t room = (uint32_t)picks[2 * idx];
+        room = room < (uint32_t)P.n_rooms ? room : (uint32_t)P.n_rooms - 1u;
+        uint32_t nf = P.rooms[room].n_free, k = (uint32_t)picks[2 * idx + 1];
+        k = k < nf ? k : nf - 1u;
+        reset_env<G>(P, env, lane, liw, room, k, episode + 1u, lut, orow);
+    } else {
+        reset_env_philox<G>(P, env, lane, liw, episode, lut, orow);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBlock) step_kernel(EngineParams P, StepIO io) {
+    __shared__ float lut[24];
+    fill_lut(lut);
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long env = gid / G;
+    if (env >= P.n_envs) return;
+    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
+    const int action = (int)io.actions[env];
+    step_env<G>(P, io, (int)env, lane, liw, action, lut, env);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(EngineParams P, int T, uint32_t t0, float *obs, float *obs_last,
+                                                         float *reward, uint8_t *done, uint8_t *actions_out,
+                                                         float *reward_scratch, uint8_t *term_scratch,
+                                                         uint8_t *trunc_scratch) {
+    __shared__ float lut[24];
+    fill_lut(lut);
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long env = gid / G;
+    if (env >= P.n_envs) return;
+    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
+    const long long N = P.n_envs;
+    for (int t = 0; t < T; t++) {
+        uint32_t u0, u1;
+        philox4x32_10(P.env_id0 + (uint32_t)env, t0 + (uint32_t)t, 0u, kStreamAction, P.seed_lo, P.seed_hi, u0, u1);
+        const int action = (int)mulhi_range(u0, 6u);
+        StepIO io;
+        io.actions = nullptr;
+        io.obs = obs ? obs + (long long)t * N * kObsDim : obs_last;
+        io.reward = reward ? reward + (long long)t * N : reward_scratch;
+        io.reward64 = nullptr;
+        io.terminated = term_scratch; io.truncated = trunc_scratch;
+        io.terminal_obs = nullptr; io.episodes = nullptr;
+        step_env<G>(P, io, (int)env, lane, liw, action, lut, env);
+        if (lane == 0) {
+            if (done) done[(long long)t * N + env] = term_scratch[env] | trunc_scratch[env];
+            if (actions_out) actions_out[(long long)t * N + env] = (uint8_t)action;
+        }
+        group_sync<G>(liw);   // lane 0's state / counter stores and every lane's S stores are visible to the next step
+    }
+}
+
+__global__ void get_state_kernel(EngineParams P, int32_t *out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.n_envs) return;
+    const EnvState s = P.states[env];
+    int32_t *o = out + (long long)env * NAV3D_STATE_INTS;
+    o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.facing;
+    o[4] = (int32_t)s.visited_count; o[5] = (int32_t)s.bump_count; o[6] = (int32_t)s.step_count;
+    o[7] = (s.flags & kNearWall) != 0; o[8] = (s.flags & kWasNearWall) != 0; o[9] = (s.flags & kLastBump) != 0;
+    o[10] = (s.flags & kDone) != 0; o[11] = s.down; o[12] = s.last_action; o[13] = s.room;
+    o[14] = (int32_t)s.episode; o[15] = s.ret_centi;
+}
+
+__global__ void get_grid_kernel(EngineParams P, int env, int16_t *out) {
+    const EnvState s = P.states[env];
+    const RoomDev R = P.rooms[s.room];
+    const int n = R.W * R.D * R.H;
+    const uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
+    const uint16_t *S = reinterpret_cast<const uint16_t *>(envk);
+    const uint8_t *C = envk + P.c_off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int z = i % R.H, y = (i / R.H) % R.D, x = i / (R.H * R.D);
+        const uint32_t sw = S[s_index(R, x, y)], ow = P.occz[R.occz_off + x * R.D + y];
+        int16_t v = -1;
+        if ((sw >> z) & 1u) v = ((ow >> z) & 1u) ? (int16_t)-2 : (int16_t)C[c_index(R, x, y, z)];
+        out[i] = v;
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------------------
+struct nav3d_engine {
+    nav3d_config cfg{};
+    int G = 8;
+    EngineParams P{};
+    std::vector<RoomDev> h_rooms;
+    std::vector<uint32_t> h_free;
+    std::vector<uint32_t> h_nwall;
+    RoomDev *d_rooms = nullptr;
+    uint16_t *d_occz = nullptr;
+    unsigned long long *d_occ64 = nullptr;
+    uint32_t *d_free = nullptr;
+    EnvState *d_states = nullptr;
+    uint8_t *d_know = nullptr;
+    size_t know_bytes = 0, room_bytes = 0;
+    // scratch for rollout / host path
+    float *d_reward = nullptr, *d_obs = nullptr;
+    uint8_t *d_term = nullptr, *d_trunc = nullptr;
+    long long *d_actions = nullptr;
+    cudaStream_t own_stream = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int set_device(const nav3d_engine *e) {
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    return NAV3D_OK;
+}
+
+void free_rooms(nav3d_engine *e) {
+    cudaFree(e->d_rooms); cudaFree(e->d_occz); cudaFree(e->d_occ64); cudaFree(e->d_free); cudaFree(e->d_know);
+    e->d_rooms = nullptr; e->d_occz = nullptr; e->d_occ64 = nullptr; e->d_free = nullptr; e->d_know = nullptr;
+    e->know_bytes = 0; e->room_bytes = 0;
+    e->h_rooms.clear(); e->h_free.clear(); e->h_nwall.clear();
+}
+
+template <typename F> int dispatch_lanes(int G, F &&f) {
+    switch (G) {
+        case 1: return f(std::integral_constant<int, 1>());
+        case 2: return f(std::integral_constant<int, 2>());
+        case 4: return f(std::integral_constant<int, 4>());
+        case 8: return f(std::integral_constant<int, 8>());
+        case 16: return f(std::integral_constant<int, 16>());
+        case 32: return f(std::integral_constant<int, 32>());
+    }
+    return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 1, 2, 4, 8, 16 or 32");
+}
+
+unsigned grid_for(long long n_groups, int G) {
+    const long long threads = n_groups * G;
+    return (unsigned)((threads + kBlock - 1) / kBlock);
+}
+
+int check_ready(const nav3d_engine *e) {
+    if (!e) return fail(NAV3D_ERR_INVALID, "engine is NULL");
+    if (e->h_rooms.empty()) return fail(NAV3D_ERR_INVALID, "no rooms loaded: call nav3d_load_rooms first");
+    return NAV3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nav3d_last_error(void) { return g_err.c_str(); }
+int nav3d_abi_version(void) { return NAV3D_ABI_VERSION; }
+
+int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
+    if (!cfg || !out) return fail(NAV3D_ERR_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    if (cfg->abi_version != NAV3D_ABI_VERSION) return fail(NAV3D_ERR_INVALID, "abi_version mismatch");
+    if (cfg->n_envs <= 0) return fail(NAV3D_ERR_INVALID, "n_envs must be positive");
+    if (cfg->env_kind != NAV3D_ENV_CUBIC)
+        return fail(NAV3D_ERR_UNSUPPORTED, "only NAV3D_ENV_CUBIC is implemented in this build");
+    if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
+        return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
+    int G = cfg->lanes_per_env == 0 ? 8 : cfg->lanes_per_env;
+    if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
+        return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(NAV3D_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    nav3d_engine *e = new (std::nothrow) nav3d_engine();
+    if (!e) return fail(NAV3D_ERR_NOMEM, "out of host memory");
+    e->cfg = *cfg;
+    e->G = G;
+    const size_t N = (size_t)cfg->n_envs;
+    cudaError_t err = cudaSuccess;
+    if ((err = cudaMalloc(&e->d_states, N * sizeof(EnvState))) != cudaSuccess ||
+        (err = cudaMemset(e->d_states, 0, N * sizeof(EnvState))) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_reward, N * sizeof(float))) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_term, N)) != cudaSuccess || (err = cudaMalloc(&e->d_trunc, N)) != cudaSuccess ||
+        (err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        nav3d_destroy(e);
+        return fail(NAV3D_ERR_CUDA, std::string("nav3d_create: ") + cudaGetErrorString(err));
+    }
+    EngineParams &P = e->P;
+    P.states = e->d_states;
+    P.n_envs = cfg->n_envs;
+    P.L = cfg->local_map_length;
+    P.env_id0 = cfg->env_id0;
+    P.seed_lo = (uint32_t)cfg->seed;
+    P.seed_hi = (uint32_t)(cfg->seed >> 32);
+    P.auto_reset = cfg->auto_reset ? 1 : 0;
+    P.crash_penalty = cfg->crash_penalty;
+    *out = e;
+    return NAV3D_OK;
+}
+
+void nav3d_destroy(nav3d_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    free_rooms(e);
+    cudaFree(e->d_states); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
+    cudaFree(e->d_obs); cudaFree(e->d_actions);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *rooms) {
+    if (!e || !rooms) return fail(NAV3D_ERR_INVALID, "engine/rooms is NULL");
+    if (n_rooms <= 0 || n_rooms > 65535) return fail(NAV3D_ERR_UNSUPPORTED, "n_rooms must be in 1..65535");
+    if (int rc = set_device(e)) return rc;
+    std::vector<RoomDev> hr((size_t)n_rooms);
+    std::vector<uint32_t> dense_off((size_t)n_rooms);
+    std::vector<int32_t> wall((size_t)n_rooms);
+    size_t n_dense = 0, n_occz = 0, n_occ64 = 0, n_free_cap = 0, max_s = 0, max_c = 0;
+    for (int i = 0; i < n_rooms; i++) {
+        const nav3d_room_desc &d = rooms[i];
+        if (!d.grid) return fail(NAV3D_ERR_INVALID, "room grid is NULL");
+        if (d.width < 1 || d.depth < 1 || d.height < 1)
+            return fail(NAV3D_ERR_ROOM, "room " + std::to_string(i) + ": non-positive dimension");
+        if (d.width > NAV3D_MAX_WIDTH || d.depth > NAV3D_MAX_DEPTH || d.height > NAV3D_MAX_HEIGHT)
+            return fail(NAV3D_ERR_UNSUPPORTED, "room " + std::to_string(i) + ": " + std::to_string(d.width) + "x" +
+                                                   std::to_string(d.depth) + "x" + std::to_string(d.height) +
+                                                   " exceeds the 64x64x16 limit of this build");
+        RoomDev &R = hr[(size_t)i];
+        R.W = (uint16_t)d.width; R.D = (uint16_t)d.depth; R.H = (uint16_t)d.height;
+        R.ntx = (uint16_t)((d.width + 3) / 4); R.nty = (uint16_t)((d.depth + 3) / 4); R.nbz = (uint16_t)((d.height + 1) / 2);
+        R.n_free = 0;
+        R.occz_off = (uint32_t)n_occz;  n_occz += (size_t)d.width * d.depth;
+        R.occx_off = (uint32_t)n_occ64; n_occ64 += (size_t)d.depth * d.height;
+        R.occy_off = (uint32_t)n_occ64; n_occ64 += (size_t)d.width * d.height;
+        R.free_off = (uint32_t)n_free_cap; n_free_cap += (size_t)d.width * d.depth * d.height;
+        dense_off[(size_t)i] = (uint32_t)n_dense; n_dense += (size_t)d.width * d.depth * d.height;
+        wall[(size_t)i] = d.wall_code;
+        max_s = std::max(max_s, (size_t)R.ntx * R.nty * 32);
+        max_c = std::max(max_c, (size_t)R.ntx * R.nty * R.nbz * 32);
+    }
+    std::vector<int8_t> dense(n_dense);
+    for (int i = 0; i < n_rooms; i++)
+        std::memcpy(dense.data() + dense_off[(size_t)i], rooms[i].grid,
+                    (size_t)rooms[i].width * rooms[i].depth * rooms[i].height);
+
+    free_rooms(e);
+    int8_t *d_dense = nullptr; uint32_t *d_off = nullptr, *d_nwall = nullptr; int32_t *d_wall = nullptr;
+    const size_t c_off = align_up(max_s, 128), stride = c_off + align_up(max_c, 128);
+    const size_t know_bytes = stride * (size_t)e->cfg.n_envs;
+    auto cleanup_tmp = [&]() { cudaFree(d_dense); cudaFree(d_off); cudaFree(d_nwall); cudaFree(d_wall); };
+#define LOAD_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess) {                                                                            \
+            cleanup_tmp(); free_rooms(e);                                                                   \
+            return fail(_e == cudaErrorMemoryAllocation ? NAV3D_ERR_NOMEM : NAV3D_ERR_CUDA,                 \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                                \
+        }                                                                                                   \
+    } while (0)
+    LOAD_TRY(cudaMalloc(&d_dense, n_dense));
+    LOAD_TRY(cudaMalloc(&d_off, sizeof(uint32_t) * n_rooms));
+    LOAD_TRY(cudaMalloc(&d_nwall, sizeof(uint32_t) * n_rooms));
+    LOAD_TRY(cudaMalloc(&d_wall, sizeof(int32_t) * n_rooms));
+    LOAD_TRY(cudaMalloc(&e->d_rooms, sizeof(RoomDev) * n_rooms));
+    LOAD_TRY(cudaMalloc(&e->d_occz, sizeof(uint16_t) * n_occz));
+    LOAD_TRY(cudaMalloc(&e->d_occ64, sizeof(unsigned long long) * n_occ64));
+    LOAD_TRY(cudaMalloc(&e->d_free, sizeof(uint32_t) * n_free_cap));
+    LOAD_TRY(cudaMalloc(&e->d_know, know_bytes));
+    LOAD_TRY(cudaMemcpy(d_dense, dense.data(), n_dense, cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemcpy(d_off, dense_off.data(), sizeof(uint32_t) * n_rooms, cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemcpy(d_wall, wall.data(), sizeof(int32_t) * n_rooms, cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemcpy(e->d_rooms, hr.data(), sizeof(RoomDev) * n_rooms, cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemset(e->d_free, 0, sizeof(uint32_t) * n_free_cap));
+    pack_rooms_kernel<<<n_rooms, 256>>>(d_dense, d_off, d_wall, e->d_rooms, e->d_occz, e->d_occ64, e->d_free, d_nwall);
+    e->launches++;
+    LOAD_TRY(cudaGetLastError());
+    e->h_free.resize(n_free_cap);
+    e->h_nwall.resize((size_t)n_rooms);
+    LOAD_TRY(cudaMemcpy(hr.data(), e->d_rooms, sizeof(RoomDev) * n_rooms, cudaMemcpyDeviceToHost));
+    LOAD_TRY(cudaMemcpy(e->h_free.data(), e->d_free, sizeof(uint32_t) * n_free_cap, cudaMemcpyDeviceToHost));
+    LOAD_TRY(cudaMemcpy(e->h_nwall.data(), d_nwall, sizeof(uint32_t) * n_rooms, cudaMemcpyDeviceToHost));
+    LOAD_TRY(cudaMemset(e->d_states, 0, sizeof(EnvState) * (size_t)e->cfg.n_envs));
+#undef LOAD_TRY
+    cleanup_tmp();
+    for (int i = 0; i < n_rooms; i++)
+        if (hr[(size_t)i].n_free == 0) {
+            free_rooms(e);
+            // the reference would fail in random.choice([]) (CubicEnv.py:462)
+            return fail(NAV3D_ERR_ROOM, "room " + std::to_string(i) + " has no free interior cell");
+        }
+    e->h_rooms = hr;
+    e->know_bytes = know_bytes;
+    e->room_bytes = sizeof(RoomDev) * n_rooms + 2 * n_occz + 8 * n_occ64 + 4 * n_free_cap;
+    EngineParams &P = e->P;
+    P.rooms = e->d_rooms; P.occz = e->d_occz; P.occ64 = e->d_occ64; P.free_cells = e->d_free;
+    P.know = e->d_know; P.env_stride = stride; P.c_off = (uint32_t)c_off; P.n_rooms = n_rooms;
+    return NAV3D_OK;
+}
+
+int nav3d_room_info(nav3d_engine *e, int32_t room, int32_t *out6) {
+    if (int rc = check_ready(e)) return rc;
+    if (!out6 || room < 0 || room >= (int)e->h_rooms.size()) return fail(NAV3D_ERR_INVALID, "bad room index");
+    const RoomDev &R = e->h_rooms[(size_t)room];
+    out6[0] = R.W; out6[1] = R.D; out6[2] = R.H; out6[3] = (int32_t)R.n_free; out6[4] = (int32_t)e->h_nwall[(size_t)room];
+    out6[5] = 0;
+    return NAV3D_OK;
+}
+
+int nav3d_room_free_cell(nav3d_engine *e, int32_t room, int32_t k, int32_t *xyz) {
+    if (int rc = check_ready(e)) return rc;
+    if (!xyz || room < 0 || room >= (int)e->h_rooms.size()) return fail(NAV3D_ERR_INVALID, "bad room index");
+    const RoomDev &R = e->h_rooms[(size_t)room];
+    if (k < 0 || (uint32_t)k >= R.n_free) return fail(NAV3D_ERR_INVALID, "free-cell index out of range");
+    const uint32_t c = e->h_free[R.free_off + (uint32_t)k];
+    xyz[0] = c & 0xff; xyz[1] = (c >> 8) & 0xff; xyz[2] = (c >> 16) & 0xff;
+    return NAV3D_OK;
+}
+
+int nav3d_obs_dim(const nav3d_engine *e) { return e ? NAV3D_OBS_DIM : 0; }
+int nav3d_num_envs(const nav3d_engine *e) { return e ? e->cfg.n_envs : 0; }
+int nav3d_lanes_per_env(const nav3d_engine *e) { return e ? e->G : 0; }
+uint64_t nav3d_launch_count(const nav3d_engine *e) { return e ? e->launches : 0; }
+size_t nav3d_device_bytes(const nav3d_engine *e) {
+    if (!e) return 0;
+    return e->know_bytes + e->room_bytes + (size_t)e->cfg.n_envs * (sizeof(EnvState) + 6);
+}
+
+int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_t *picks, float *obs, void *stream) {
+    if (int rc = check_ready(e)) return rc;
+    if (n < 0 || (!env_ids && n > e->cfg.n_envs)) return fail(NAV3D_ERR_INVALID, "n out of range");
+    if (n == 0) return NAV3D_OK;
+    if (obs && ((uintptr_t)obs & 15u)) return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
+    if (int rc = set_device(e)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = dispatch_lanes(e->G, [&](auto g) {
+        constexpr int G = decltype(g)::value;
+        reset_kernel<G><<<grid_for(n, G), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
+        return NAV3D_OK;
+    });
+    if (rc) return rc;
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NAV3D_OK;
+}
+
+int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, double *reward64,
+               uint8_t *terminated, uint8_t *truncated, float *terminal_obs, nav3d_episode *episodes, void *stream) {
+    if (int rc = check_ready(e)) return rc;
+    if (!actions || !obs || !reward || !terminated || !truncated)
+        return fail(NAV3D_ERR_INVALID, "actions, obs, reward, terminated and truncated are required");
+    if (((uintptr_t)obs & 15u) || (terminal_obs && ((uintptr_t)terminal_obs & 15u)))
+        return fail(NAV3D_ERR_INVALID, "obs / terminal_obs must be 16-byte aligned");
+    if (int rc = set_device(e)) return rc;
+    StepIO io;
+    io.actions = reinterpret_cast<const long long *>(actions);
+    io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = terminated; io.truncated = truncated;
+    io.terminal_obs = terminal_obs; io.episodes = episodes;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = dispatch_lanes(e->G, [&](auto g) {
+        constexpr int G = decltype(g)::value;
+        step_kernel<G><<<grid_for(e->cfg.n_envs, G), kBlock, 0, s>>>(e->P, io);
+        return NAV3D_OK;
+    });
+    if (rc) return rc;
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NAV3D_OK;
+}
+
+int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, uint8_t *terminated,
+                    uint8_t *truncated) {
+    if (int rc = check_ready(e)) return rc;
+    if (!actions || !obs || !reward || !terminated || !truncated) return fail(NAV3D_ERR_INVALID, "NULL host buffer");
+    if (int rc = set_device(e)) return rc;
+    const size_t N = (size_t)e->cfg.n_envs;
+    if (!e->d_obs) CUDA_TRY(cudaMalloc(&e->d_obs, N * kObsDim * sizeof(float)));
+    if (!e->d_actions) CUDA_TRY(cudaMalloc(&e->d_actions, N * sizeof(long long)));
+    cudaStream_t s = e->own_stream;
+    CUDA_TRY(cudaMemcpyAsync(e->d_actions, actions, N * sizeof(long long), cudaMemcpyHostToDevice, s));
+    int rc = nav3d_step(e, reinterpret_cast<const int64_t *>(e->d_actions), e->d_obs, e->d_reward, nullptr, e->d_term,
+                        e->d_trunc, nullptr, nullptr, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(obs, e->d_obs, N * kObsDim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(terminated, e->d_term, N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(truncated, e->d_trunc, N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NAV3D_OK;
+}
+
+int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, float *obs_last, float *reward,
+                         uint8_t *done, uint8_t *actions_out, void *stream) {
+    if (int rc = check_ready(e)) return rc;
+    if (T < 0) return fail(NAV3D_ERR_INVALID, "T must be >= 0");
+    if (T == 0) return NAV3D_OK;
+    if (!obs && !obs_last) return fail(NAV3D_ERR_INVALID, "one of obs / obs_last is required");
+    if ((obs && ((uintptr_t)obs & 15u)) || (obs_last && ((uintptr_t)obs_last & 15u)))
+        return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
+    if (int rc = set_device(e)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = dispatch_lanes(e->G, [&](auto g) {
+        constexpr int G = decltype(g)::value;
+        rollout_kernel<G><<<grid_for(e->cfg.n_envs, G), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward, done,
+                                                                       actions_out, e->d_reward, e->d_term, e->d_trunc);
+        return NAV3D_OK;
+    });
+    if (rc) return rc;
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NAV3D_OK;
+}
+
+int nav3d_get_state(nav3d_engine *e, int32_t *state, void *stream) {
+    if (int rc = check_ready(e)) return rc;
+    if (!state) return fail(NAV3D_ERR_INVALID, "state is NULL");
+    if (int rc = set_device(e)) return rc;
+    get_state_kernel<<<(e->cfg.n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->P, state);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NAV3D_OK;
+}
+
+int nav3d_get_grid(nav3d_engine *e, int32_t env, int16_t *grid, void *stream) {
+    if (int rc = check_ready(e)) return rc;
+    if (!grid || env < 0 || env >= e->cfg.n_envs) return fail(NAV3D_ERR_INVALID, "bad env index / NULL grid");
+    if (int rc = set_device(e)) return rc;
+    get_grid_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(e->P, env, grid);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NAV3D_OK;
+}
+
+size_t nav3d_snapshot_bytes(const nav3d_engine *e) {
+    if (!e || e->h_rooms.empty()) return 0;
+    return (size_t)e->cfg.n_envs * sizeof(EnvState) + e->know_bytes;
+}
+
+int nav3d_snapshot(nav3d_engine *e, void *host_buf, size_t bytes) {
+    if (int rc = check_ready(e)) return rc;
+    if (!host_buf || bytes != nav3d_snapshot_bytes(e)) return fail(NAV3D_ERR_INVALID, "snapshot buffer size mismatch");
+    if (int rc = set_device(e)) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t sb = (size_t)e->cfg.n_envs * sizeof(EnvState);
+    CUDA_TRY(cudaMemcpy(host_buf, e->d_states, sb, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy((char *)host_buf + sb, e->d_know, e->know_bytes, cudaMemcpyDeviceToHost));
+    return NAV3D_OK;
+}
+
+int nav3d_restore(nav3d_engine *e, const void *host_buf, size_t bytes) {
+    if (int rc = check_ready(e)) return rc;
+    if (!host_buf || bytes != nav3d_snapshot_bytes(e)) return fail(NAV3D_ERR_INVALID, "snapshot buffer size mismatch");
+    if (int rc = set_device(e)) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t sb = (size_t)e->cfg.n_envs * sizeof(EnvState);
+    CUDA_TRY(cudaMemcpy(e->d_states, host_buf, sb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->d_know, (const char *)host_buf + sb, e->know_bytes, cudaMemcpyHostToDevice));
+    return NAV3D_OK;
+}
+
+}  // extern "C"

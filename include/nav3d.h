@@ -1,0 +1,178 @@
+/*
+ * nav3d.h — C ABI of libnav3d_b200.so: GPU-resident, batched voxel-navigation environments for NVIDIA B200 (sm_100a).
+ *
+ * The reference (Noimps/3D-Navigation-Reinforcement-Learning) has no native boundary: its environment is the Python
+ * class envs/CubicEnv.py::GridAgent, driven one OS process per env through stable-baselines3's SubprocVecEnv
+ * (train/Grid_Train.py:170-173, :191-192).  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer documented as DEVICE points into the memory of the engine's CUDA device
+ *     (e.g. torch.Tensor.data_ptr()); HOST pointers are ordinary process memory.
+ *   - `stream` is a CUDA stream handle (cudaStream_t / CUstream) passed as void*; NULL = the legacy default stream.
+ *     Calls that take a stream are asynchronous on it and never synchronise the host.
+ *   - return value: NAV3D_OK (0) or a negative nav3d_status; nav3d_last_error() gives the message of the calling
+ *     thread's last failure.  Nothing throws across this boundary.
+ *   - one engine per device (or several); calls on one engine must be serialised by the caller; engines are independent.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with NAV3D_ERR_CUDA.
+ *
+ * Limits (checked, NAV3D_ERR_UNSUPPORTED): room width, depth <= 64, height <= 16 (the reference's largest shipped room
+ * is 48x32x12); local_map_length in 1..255; at most 65535 rooms per engine.
+ *
+ * Random streams (counter-based Philox4x32-10, Salmon et al. SC'11) — documented because the oracle restates them:
+ *   key = (seed & 0xffffffff, seed >> 32);  counter = (global_env_id, index, 0, stream_tag)
+ *   stream_tag 0x52455345: index = episode number of that env (0 for the first reset); output word 0 -> room index,
+ *                          word 1 -> index k into the room's list of free interior cells (x-major, then y, then z —
+ *                          the order envs/CubicEnv.py:450-457 builds possible_start_pose in)
+ *   stream_tag 0x41435449: index = rollout step t; output word 0 -> action
+ *   a 32-bit word u maps to [0, n) as (u * n) >> 32.
+ *   global_env_id = config.env_id0 + local env index, so results do not depend on how envs are sharded over GPUs.
+ */
+#ifndef NAV3D_H
+#define NAV3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAV3D_ABI_VERSION 1
+#define NAV3D_OBS_DIM 80          /* envs/CubicEnv.py:58-62 */
+#define NAV3D_NUM_ACTIONS 6       /* envs/CubicEnv.py:56   */
+#define NAV3D_STATE_INTS 16       /* ints per env written by nav3d_get_state */
+#define NAV3D_MAX_WIDTH 64
+#define NAV3D_MAX_DEPTH 64
+#define NAV3D_MAX_HEIGHT 16
+
+typedef enum {
+    NAV3D_OK = 0,
+    NAV3D_ERR_INVALID = -1,       /* bad argument (NULL, out of range, engine without rooms, ...) */
+    NAV3D_ERR_UNSUPPORTED = -2,   /* outside the limits above */
+    NAV3D_ERR_CUDA = -3,          /* CUDA runtime error; message carries cudaGetErrorString */
+    NAV3D_ERR_NOMEM = -4,
+    NAV3D_ERR_ROOM = -5           /* malformed room (no free interior cell, bad dims) */
+} nav3d_status;
+
+typedef enum {
+    NAV3D_ENV_CUBIC = 0,          /* envs/CubicEnv.py::GridAgent  — 80 f32 observations, visit-count knowledge grid   */
+    NAV3D_ENV_SIMPLE = 1          /* envs/simpleEnv.py::GridAgent — 6L+7 f32 observations, ternary knowledge grid     */
+} nav3d_env_kind;
+
+typedef struct nav3d_engine nav3d_engine;
+
+/* Constructor arguments.  Mirrors the kwargs of GridAgent.__init__ (envs/CubicEnv.py:17-29) that affect dynamics. */
+typedef struct {
+    int32_t abi_version;          /* = NAV3D_ABI_VERSION */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t n_envs;               /* environments held by this engine (this GPU's shard) */
+    int32_t env_kind;             /* nav3d_env_kind */
+    int32_t local_map_length;     /* ray length L (CubicEnv.py:25; 10 in train/Grid_Train.py:36) */
+    int32_t auto_reset;           /* 1: finished envs reset inside nav3d_step (SB3 VecEnv contract), 0: plain gym */
+    int32_t lanes_per_env;        /* threads cooperating on one env: 1,2,4,8,16,32; 0 = engine default */
+    uint32_t env_id0;             /* global id of local env 0 (sharding) */
+    uint64_t seed;                /* Philox key */
+    double crash_penalty;         /* CubicEnv.py:28, -2.0 */
+    double cell_size;             /* CubicEnv.py:24 / simpleEnv.py:22, 0.25 (simpleEnv distances only) */
+} nav3d_config;
+
+/* One parsed room: what load_room leaves in self.grid (envs/CubicEnv.py:421-438), as int8, C order [x][y][z].
+ * A cell equal to `wall_code` is a wall: -2 for CubicEnv (after the reference's 2 -> -2 rewrite, :434), 2 for simpleEnv. */
+typedef struct {
+    int32_t width, depth, height;
+    int32_t wall_code;
+    const int8_t *grid;           /* HOST, width*depth*height bytes */
+} nav3d_room_desc;
+
+/* Written by nav3d_step only for envs whose episode ended in that step (Monitor's info["episode"] plus the
+ * attributes train/evaluate_grid.py:216-218 reads). 32 bytes. */
+typedef struct {
+    float episode_return;         /* sum of rewards of the finished episode */
+    int32_t length;               /* step_count at the end */
+    int32_t bumps;                /* bump_count */
+    int32_t visited;              /* visited_count */
+    int32_t total_free;           /* total_free_cells of the finished room */
+    int32_t room;                 /* room index of the finished episode */
+    int32_t terminated;           /* 1 if >= 84 % explored (CubicEnv) / goal reached (simpleEnv) */
+    int32_t truncated;
+} nav3d_episode;
+
+const char *nav3d_last_error(void);
+int nav3d_abi_version(void);
+
+/* GridAgent.__init__ (envs/CubicEnv.py:17-74).  Allocates nothing per room yet. */
+int nav3d_create(const nav3d_config *cfg, nav3d_engine **out);
+void nav3d_destroy(nav3d_engine *e);
+
+/* The room table: replaces the per-reset text parse + free-cell scan of load_room (envs/CubicEnv.py:402-459).
+ * Dense grids are uploaded once; a CUDA kernel packs each room into bit-packed occupancy words (three orientations)
+ * and builds the ordered free-cell list; per-env knowledge storage is sized for the largest room.
+ * After this call every env must be reset before it is stepped. */
+int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *rooms);
+/* out6 = width, depth, height, total_free_cells (= max_steps, CubicEnv.py:459), n_wall_cells, reserved.  Synchronises. */
+int nav3d_room_info(nav3d_engine *e, int32_t room, int32_t *out6);
+/* HOST out: the k-th free interior cell of `room` as x,y,z (possible_start_pose[k], CubicEnv.py:450-457). Synchronises. */
+int nav3d_room_free_cell(nav3d_engine *e, int32_t room, int32_t k, int32_t *xyz);
+int nav3d_obs_dim(const nav3d_engine *e);
+int nav3d_num_envs(const nav3d_engine *e);
+int nav3d_lanes_per_env(const nav3d_engine *e);
+
+/* GridAgent.reset (envs/CubicEnv.py:77-108) for a set of envs.
+ *   env_ids : DEVICE int32[n] or NULL = envs 0..n-1 (then n must be <= n_envs)
+ *   picks   : DEVICE int32[n][2] = (room index, k-th free cell) per listed env — the two random.choice draws of
+ *             load_room (:407, :462; for simpleEnv a third column would be the goal: see nav3d_reset_simple) —
+ *             or NULL = draw them from the env's Philox reset stream
+ *   obs     : DEVICE f32[n_envs][obs_dim]; rows of the listed envs are written; may be NULL */
+int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_t *picks, float *obs, void *stream);
+
+/* GridAgent.step (envs/CubicEnv.py:110-132) for all envs of the engine, plus — when auto_reset — the
+ * SubprocVecEnv worker's "if done: stash terminal_observation, reset" (SURVEY §8b B2).
+ *   actions      : DEVICE int64[n_envs], values 0..5
+ *   obs          : DEVICE f32[n_envs][obs_dim], 16-byte aligned (a [t,:,:] slice of a rollout buffer is fine)
+ *   reward       : DEVICE f32[n_envs]  (the f64 reward of compute_reward rounded to f32, as SB3 stores it)
+ *   reward64     : DEVICE f64[n_envs] or NULL
+ *   terminated, truncated : DEVICE u8[n_envs]
+ *   terminal_obs : DEVICE f32[n_envs][obs_dim] or NULL; written only for envs that were auto-reset
+ *   episodes     : DEVICE nav3d_episode[n_envs] or NULL; written only for envs whose episode ended */
+int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, double *reward64,
+               uint8_t *terminated, uint8_t *truncated, float *terminal_obs, nav3d_episode *episodes, void *stream);
+
+/* Same step through HOST buffers: the call a CPU-side trainer (SB3's VecEnv.step_wait, Grid_Train.py:228) makes.
+ * Copies actions host->device, steps, copies obs/reward/terminated/truncated device->host and waits for them. */
+int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, uint8_t *terminated,
+                    uint8_t *truncated);
+
+/* T fused steps with uniform random actions from the env's Philox action stream (indices t0 .. t0+T-1):
+ * the "synthetic random-action rollout" of BASELINE.json.  One launch; each env's steps run back to back.
+ *   obs    : DEVICE f32[T][n_envs][obs_dim] or NULL (then only the last observation is kept in obs_last)
+ *   obs_last: DEVICE f32[n_envs][obs_dim] or NULL
+ *   reward : DEVICE f32[T][n_envs] or NULL;  done : DEVICE u8[T][n_envs] or NULL (terminated | truncated)
+ *   actions_out : DEVICE u8[T][n_envs] or NULL */
+int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, float *obs_last, float *reward,
+                         uint8_t *done, uint8_t *actions_out, void *stream);
+
+/* Integer state of every env (attributes read by the reference's callers: get_position CubicEnv.py:399-400,
+ * visited_count/bump_count/done evaluate_grid.py:216-218, ...).  DEVICE int32[n_envs][NAV3D_STATE_INTS]:
+ *  0 x  1 y  2 z  3 facing  4 visited_count  5 bump_count  6 step_count  7 near_wall  8 was_near_wall  9 last_bump
+ * 10 done  11 cells_insight_down  12 last_action  13 room index  14 episode number  15 return so far, in 1/100 units,
+ *    excluding crash penalties */
+int nav3d_get_state(nav3d_engine *e, int32_t *state, void *stream);
+/* self.internal_grid of one env (CubicEnv.py:84-85) rebuilt from the packed representation, DEVICE int16
+ * [width][depth][height] of the env's current room (C order).  Visit counters saturate at 255. */
+int nav3d_get_grid(nav3d_engine *e, int32_t env, int16_t *grid, void *stream);
+
+/* Checkpoint / restore of the complete mutable engine state (scalars + knowledge grids), HOST buffers. */
+size_t nav3d_snapshot_bytes(const nav3d_engine *e);
+int nav3d_snapshot(nav3d_engine *e, void *host_buf, size_t bytes);
+int nav3d_restore(nav3d_engine *e, const void *host_buf, size_t bytes);
+
+/* Number of CUDA kernels this library has launched since the engine was created (bench.py's gpu_launches). */
+uint64_t nav3d_launch_count(const nav3d_engine *e);
+/* Bytes of device memory the engine holds. */
+size_t nav3d_device_bytes(const nav3d_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAV3D_H */
