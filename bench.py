@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of batched CubicEnv.step on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N --steps K --warmup W] [--workload c4|c2|c3] [--impl reference]
+
+A "step" is ONE nav3d_step launch over every env of the workload (one pass of the hot path over one batch):
+  value     device-resident: actions already in HBM, observations written into an HBM rollout ring; CUDA-event timed
+  e2e       the same step through nav3d_step_host with pinned HOST buffers (actions H2D, obs/reward/flags D2H, every step)
+  roofline  algorithmic bytes (592 B per env-step, SURVEY §8d / DESIGN.md §5) x envs per launch / mean launch duration
+  cpu_baseline  the Python port of the reference env (oracle/py_cubic.py) on this box's host cores, plus the C oracle
+Workloads (BASELINE.json configs): c4 = 2^20 envs sharded over the N GPUs (default, the config the 1/2/4/8 metric is
+quoted on), c2 = 4096 envs on P1_training, c3 = 65536 envs on P2+P3_training.  Under torchrun every rank holds its own
+env shard and room table; there is no collective on the data path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+import _nav3d_path  # noqa: E402,F401
+
+B_ALG = {10: 592, 4: 516}          # algorithmic bytes per env-step, SURVEY.md §8d
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def workload_spec(name):
+    if name == "c4":
+        return dict(name="c4", envs_total=1 << 20, room_dirs=["P1_training"], L=10, scaling="strong",
+                    desc="BASELINE configs[3]: 2^20 CubicEnv envs env-sharded over the GPUs, rooms/P1_training (5 rooms), "
+                         "L=10, uniform random actions, auto-reset")
+    if name == "c2":
+        return dict(name="c2", envs_total=4096, room_dirs=["P1_training"], L=10, scaling="weak",
+                    desc="BASELINE configs[1]: 4096 CubicEnv envs per GPU, rooms/P1_training, L=10, random actions")
+    if name == "c3":
+        return dict(name="c3", envs_total=65536, room_dirs=["P2_training", "P3_training"], L=10, scaling="weak",
+                    desc="BASELINE configs[2]: 65536 CubicEnv envs per GPU, rooms/P2_training + P3_training (42 rooms), L=10")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def load_rooms(spec):
+    from nav3d.rooms import load_room_dir
+    rooms = []
+    for d in spec["room_dirs"]:
+        rooms += load_room_dir(ROOT / "rooms" / d, sort=True)
+    return rooms
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------------------------------
+def python_port_rate(grids, L, steps_per_worker, workers):
+    """N worker processes, one env each (the reference's SubprocVecEnv shape); returns (steps/s summed, wall seconds)."""
+    import multiprocessing as mp
+    from oracle.py_cubic import worker_rollout
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(worker_rollout, [(grids, L, steps_per_worker, 42 + i) for i in range(workers)])
+    wall = time.perf_counter() - t0
+    return sum(n / t for n, t in res), wall
+
+
+def c_port_rate(rooms, L, n_envs, T, threads):
+    from oracle import c_oracle
+    orooms = [c_oracle.OracleRoom(r.grid, -2) for r in rooms]
+    ov = c_oracle.OracleVec(n_envs, orooms, L, -2.0, 0, 0, True)
+    c_oracle.set_threads(threads)
+    ov.reset()
+    ov.rollout_random(8, 0)
+    t0 = time.perf_counter()
+    n, _, _ = ov.rollout_random(T, 8)
+    dt = time.perf_counter() - t0
+    c_oracle.set_threads(1)
+    return n / dt
+
+
+def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path, all host cores.  The reference is a Python
+    class and /root/reference does not travel to the GPU box, so this times oracle/py_cubic.py (the Python port pinned to
+    the reference's golden traces), one env per worker process like the reference's SubprocVecEnv."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = workload_spec(args.workload)
+    rooms = load_rooms(spec)
+    grids = [r.grid.astype(int) for r in rooms]
+    cores = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    # each "step" = every worker advances its env by S env-steps; S sized so the whole run takes about a minute
+    S = int(max(20, min(4000, 60.0 * 7000.0 / max(1, K + W))))
+    python_port_rate(grids, spec["L"], max(1, W * S // 4), cores)          # warm-up (fork, page-in)
+    t0 = time.perf_counter()
+    rate, wall = python_port_rate(grids, spec["L"], K * S, cores)
+    one, _ = python_port_rate(grids, spec["L"], min(K * S, 20000), 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
+        "dtype": "python int/f64 (NumPy)", "data": "synthetic",
+        "config": {"workload": spec["desc"], "sample": f"{cores} worker processes x 1 env, {S} env-steps per worker per step"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"oracle/py_cubic.py, {cores} processes x {K * S} random-action steps with reset on done",
+                         "one_process": one},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def time_steps(eng, n, steps, warmup, torch, dist, world, lanes_note=None, ring=4, act_rows=16, seed=0):
+    """Device-resident timing of `steps` nav3d_step launches.  Returns (ms_total_max_over_ranks, ms_total_local, launches)."""
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(1234 + seed)
+    actions = torch.randint(0, 6, (act_rows, n), generator=g, device=dev, dtype=torch.int64)
+    obs = torch.empty((ring, n, 80), dtype=torch.float32, device=dev)
+    rew = torch.empty(n, dtype=torch.float32, device=dev)
+    te = torch.empty(n, dtype=torch.uint8, device=dev)
+    tr = torch.empty(n, dtype=torch.uint8, device=dev)
+    eng.reset(obs[0])
+    for t in range(warmup):
+        eng.step(actions[t % act_rows], obs[t % ring], rew, te, tr)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for t in range(steps):
+        eng.step(actions[t % act_rows], obs[t % ring], rew, te, tr)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_local = e0.elapsed_time(e1)
+    ms = ms_local
+    if world > 1:
+        dist.barrier()
+        tmax = torch.tensor([ms_local], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    return ms, ms_local, eng.launch_count - l0
+
+
+def time_e2e(eng, n, steps, torch, dist, world):
+    dev = eng.device
+    a = [torch.randint(0, 6, (n,), dtype=torch.int64).pin_memory() for _ in range(4)]
+    obs = torch.empty((n, 80), dtype=torch.float32).pin_memory()
+    rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    te = torch.empty(n, dtype=torch.uint8).pin_memory()
+    tr = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(3):
+        eng.step_host(a[t % 4], obs, rew, te, tr)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in range(steps):
+        eng.step_host(a[t % 4], obs, rew, te, tr)
+    torch.cuda.synchronize(dev)
+    sec = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+        tmax = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sec = float(tmax.item())
+    checksum = float(rew.sum())
+    return sec, n * 8, n * (80 * 4 + 4 + 1 + 1), checksum
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="nav3d", choices=["nav3d", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3"])
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = engine default)")
+    ap.add_argument("--envs", type=int, default=0, help="override the total env count")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads and the CPU baseline")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nav3d import Engine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; nav3d has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    spec = workload_spec(args.workload)
+    if args.envs:
+        spec["envs_total"] = args.envs
+    rooms = load_rooms(spec)
+    L = spec["L"]
+    if spec["scaling"] == "strong":
+        n_total = spec["envs_total"]
+        n_local = n_total // world
+    else:
+        n_local = spec["envs_total"]
+        n_total = n_local * world
+    eng = Engine(n_local, rooms, local_map_length=L, seed=2024, env_id0=rank * n_local, device=local_rank,
+                 lanes_per_env=args.lanes)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, ms_local, launches = time_steps(eng, n_local, args.steps, args.warmup, torch, dist, world)
+    clocks = sampler.stop() if rank == 0 else None
+    value = n_total * args.steps / (ms / 1e3)
+
+    e2e_steps = max(3, min(args.e2e_steps, args.steps))
+    sec, h2d, d2h, _ = time_e2e(eng, n_local, e2e_steps, torch, dist, world)
+    e2e_value = n_total * e2e_steps / sec
+
+    # roofline of the dominant kernel (step_kernel): measured on this rank's own stream with CUDA events
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    balg = B_ALG.get(L, 334 + 64 + 64 + 12 * L + 2 + (6 * L + 1 + 7) // 8)
+    launch_ms = ms_local / args.steps
+    achieved = balg * n_local / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(f"{spec['name']}_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": f"step_kernel<{eng.lanes_per_env}>",
+                "algorithmic_bytes_per_env_step": balg, "env_steps_per_launch": n_local,
+                "launch_ms": launch_ms, "peak_source": peak_src}
+
+    extra = {}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        # secondary workloads, same timing method (short)
+        del eng
+        torch.cuda.empty_cache()
+        for wl in ("c2", "c3"):
+            if wl == spec["name"]:
+                continue
+            s2 = workload_spec(wl)
+            r2 = load_rooms(s2)
+            e2 = Engine(s2["envs_total"], r2, local_map_length=s2["L"], seed=2024, device=local_rank,
+                        lanes_per_env=args.lanes)
+            k2 = 2000
+            m2, _, _ = time_steps(e2, s2["envs_total"], k2, 50, torch, dist, 1)
+            extra[wl] = {"workload": s2["desc"], "value": s2["envs_total"] * k2 / (m2 / 1e3), "unit": UNIT,
+                         "ms_per_step": m2 / k2, "steps": k2,
+                         "roofline_frac": B_ALG[10] * s2["envs_total"] / (m2 / k2 * 1e-3) / 1e9 / peak}
+            del e2
+            torch.cuda.empty_cache()
+        # fused random-action rollout kernel (one launch = T steps of every env), c4 size
+        try:
+            s4 = workload_spec("c4")
+            e4 = Engine(s4["envs_total"], load_rooms(s4), local_map_length=10, seed=2024, device=local_rank,
+                        lanes_per_env=args.lanes)
+            n4, T = s4["envs_total"], 32
+            obs = e4.reset()
+            rew = torch.empty((T, n4), dtype=torch.float32, device=e4.device)
+            done = torch.empty((T, n4), dtype=torch.uint8, device=e4.device)
+            e4.rollout_random(T, 0, obs_last=obs, reward=rew, done=done)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            reps = 8
+            for i in range(reps):
+                e4.rollout_random(T, T * (i + 1), obs_last=obs, reward=rew, done=done)
+            ev1.record()
+            torch.cuda.synchronize()
+            mr = ev0.elapsed_time(ev1)
+            extra["fused_rollout_c4"] = {"value": n4 * T * reps / (mr / 1e3), "unit": UNIT, "T": T,
+                                         "note": "nav3d_rollout_random: on-device Philox actions, last observation + "
+                                                 "per-step reward/done kept"}
+            del e4
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            extra["fused_rollout_c4"] = {"error": str(ex)}
+        # CPU baseline on this box's host cores (bounded sample)
+        cores = os.cpu_count() or 1
+        grids = [r.grid.astype(int) for r in rooms]
+        per_worker = 30000
+        py_all, wall = python_port_rate(grids, L, per_worker, cores)
+        py_one, _ = python_port_rate(grids, L, 20000, 1)
+        c_all = c_port_rate(rooms, L, 4096, 100, cores)
+        c_one = c_port_rate(rooms, L, 512, 100, 1)
+        cpu_baseline = {"value": py_all, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"oracle/py_cubic.py (Python port of the reference env, pinned to its golden traces): {cores} "
+                                  f"worker processes x 1 env x {per_worker} random-action steps, reset on done ({wall:.1f} s)",
+                        "one_process": py_one,
+                        "c_port": {"value": c_all, "cores": cores, "one_thread": c_one,
+                                   "sample": "oracle/nav3d_oracle.c: 4096 envs x 100 steps, pthreads"}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
+            "dtype": "u8/u16 bit-packed state, f32 obs, f64 reward", "data": "synthetic",
+            "config": {"workload": spec["desc"], "envs_total": n_total, "envs_per_gpu": n_local,
+                       "lanes_per_env": roofline["kernel"], "local_map_length": L,
+                       "l2": f"inputs larger than L2: {n_local * 21504 / 2**30:.1f} GiB of per-env knowledge per GPU vs 126 MB L2; no flush needed"
+                             if n_local * 21504 > 4 * 126e6 else
+                             "working set is L2-resident by design for this workload (not flushed: a trainer re-steps the same envs)",
+                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "steps": e2e_steps, "api": "nav3d_step_host (pinned host buffers, per-step H2D actions + D2H obs/reward/flags)"},
+            "gpu_launches": launches * world,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,7 +44,7 @@ def lib():
         "orc_action": (I, [C.c_uint64, C.c_uint32, C.c_uint32]),
         "orc_vec_create": (P, [I, I, P, I, D, C.c_uint64, C.c_uint32, I]), "orc_vec_destroy": (None, [P]),
         "orc_vec_env": (P, [P, I]), "orc_vec_room_idx": (I, [P, I]), "orc_vec_episode": (C.c_uint32, [P, I]),
-        "orc_vec_reset": (None, [P, P, P]),
+        "orc_vec_reset": (None, [P, P, P]), "orc_vec_set_ids": (None, [P, P]), "orc_vec_state": (None, [P, P]),
         "orc_vec_step": (None, [P, P, P, P, P, P, P, P, P, P, P]),
         "orc_vec_rollout_random": (C.c_long, [P, I, C.c_uint32, P, P]),
         "orc_set_threads": (None, [I]), "orc_get_threads": (I, []), "orc_hw_threads": (I, []),
@@ -227,13 +227,14 @@ class OracleVec:
     def state(self) -> np.ndarray:
         """int64 [n, 15]: CUBIC_STATE columns + room index + episode number."""
         out = np.zeros((self.n, 15), dtype=np.int64)
-        tmp = np.zeros(13, dtype=np.int64)
-        for i in range(self.n):
-            lib().orc_cubic_state(lib().orc_vec_env(self.h, i), _p(tmp))
-            out[i, :13] = tmp
-            out[i, 13] = lib().orc_vec_room_idx(self.h, i)
-            out[i, 14] = lib().orc_vec_episode(self.h, i)
+        lib().orc_vec_state(self.h, _p(out))
         return out
+
+    def set_ids(self, ids):
+        """Local env i plays global env ``ids[i]`` (to check a sample of a larger sharded job)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert ids.shape == (self.n,)
+        lib().orc_vec_set_ids(self.h, _p(ids))
 
     def grid(self, i: int) -> np.ndarray:
         room = self.rooms[lib().orc_vec_room_idx(self.h, i)]

