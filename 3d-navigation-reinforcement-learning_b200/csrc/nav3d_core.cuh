@@ -214,12 +214,94 @@ struct ObsScalars {
 template <int G>
 NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z,
                       const Rays &r, int centre_count, bool write_seen, const ObsScalars &sc, const float *lut,
-                      float *obs_row) {
-    uint16_t *S = reinterpret_cast<uint16_t *>(envk);
-    const uint8_t *C = envk + P.c_off;
+                      float *__restrict__ obs_row) {
+    uint16_t *__restrict__ S = reinterpret_cast<uint16_t *>(envk);
+    const uint8_t *__restrict__ C = envk + P.c_off;
     const uint32_t zbit = 1u << z;
 
-    // Step 1 (:264-266): mark every cell the six rays examined as seen.
+    if (obs_row != nullptr) {
+        // Step 2 (:270-275): the 4x4x4 window, one (x,y) column = one float4 of the observation.  All loads of a batch
+        // of columns are issued before any of them is used so that they overlap (memory-level parallelism).
+        constexpr int CPL = (16 + G - 1) / G;          // window columns per lane
+        constexpr int CH = CPL > 4 ? 4 : CPL;          // columns per batch
+        const int zb0 = (z - 2) >> 1;                  // first z-brick of the window (may be -1)
+        const int zsh = ((z - 2) - 2 * zb0) * 8;       // bit offset of cell z-2 inside the 3-brick column word (0 or 8)
+        const float unknown = lut[1];
+#pragma unroll
+        for (int q0 = 0; q0 < CPL; q0 += CH) {
+            uint32_t sw[CH], ow[CH];
+            unsigned long long cw[CH];
+            bool inb[CH];
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int j = lane + (q0 + q) * G;
+                const int cx = x + (j >> 2) - 2, cy = y + (j & 3) - 2;
+                inb[q] = j < 16 && cx >= 0 && cx < R.W && cy >= 0 && cy < R.D;
+                sw[q] = 0; ow[q] = 0; cw[q] = 0;
+                if (inb[q]) {
+                    sw[q] = S[s_index(R, cx, cy)];
+                    ow[q] = ldg(P.occz + R.occz_off + (uint32_t)(cx * R.D + cy));
+                    const uint16_t *cp = reinterpret_cast<const uint16_t *>(C + c_index(R, cx, cy, 0));   // brick 0 of the column
+                    unsigned long long w = 0;
+                    if (zb0 >= 0) w = cp[zb0 * 16];                                          // bricks are 32 B = 16 u16 apart
+                    if (zb0 + 1 < R.nbz) w |= (unsigned long long)cp[(zb0 + 1) * 16] << 16;
+                    if (zsh && zb0 + 2 < R.nbz) w |= (unsigned long long)cp[(zb0 + 2) * 16] << 32;
+                    cw[q] = w;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CH; q++) {
+                const int j = lane + (q0 + q) * G;
+                if (j >= 16) continue;
+                const int cx = x + (j >> 2) - 2, cy = y + (j & 3) - 2;
+                float out[4];
+                out[0] = out[1] = out[2] = out[3] = unknown;
+                if (inb[q]) {
+                    uint32_t s = sw[q];
+                    if (cy == y && cx >= r.x0 && cx <= r.x1) s |= (cx == x) ? r.zmask : zbit;
+                    if (cx == x && cy >= r.y0 && cy <= r.y1) s |= zbit;
+                    const bool centre_col = (cx == x && cy == y);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int cz = z - 2 + k;
+                        if (cz >= 0 && cz < R.H && ((s >> cz) & 1u)) {
+                            if ((ow[q] >> cz) & 1u) out[k] = lut[0];               // known wall: (-2+2)/22
+                            else {
+                                int c = (int)((cw[q] >> (zsh + 8 * k)) & 0xffu);
+                                if (centre_col && k == 2) c = centre_count;
+                                out[k] = lut[2 + imin(c, 20)];
+                            }
+                        }
+                    }
+                }
+                reinterpret_cast<float4 *>(obs_row)[j] = make_float4(out[0], out[1], out[2], out[3]);
+            }
+        }
+        // Steps 3-6: the 9 scalars + zero padding = 4 more float4 (:279-307)
+        for (int j = 16 + lane; j < 20; j += G) {
+            float4 v;
+            if (j == 16) {
+                v.x = sc.facing == 0 ? 1.f : 0.f; v.y = sc.facing == 1 ? 1.f : 0.f;
+                v.z = sc.facing == 2 ? 1.f : 0.f; v.w = sc.facing == 3 ? 1.f : 0.f;
+            } else if (j == 17) {
+                // float(k)/5, count/L and visited/total are f64 quotients rounded to f32 in the reference (:284-291); for
+                // integers below 2^24 that equals the correctly rounded f32 quotient (53 >= 2*24+2, Figueroa 1995).
+                v.x = fdiv_rn((float)sc.last_action, 5.0f);
+                v.y = (float)sc.was_near_wall;
+                v.z = (float)sc.last_bump;
+                v.w = fdiv_rn((float)sc.down, (float)P.L);
+            } else if (j == 18) {
+                v.x = fdiv_rn((float)sc.visited, (float)sc.total_free);
+                v.y = v.z = v.w = 0.f;
+            } else {
+                v.x = v.y = v.z = v.w = 0.f;
+            }
+            reinterpret_cast<float4 *>(obs_row)[j] = v;
+        }
+    }
+
+    // Step 1 (:264-266): mark every cell the six rays examined as seen.  (Done after the gather in program order — the
+    // gather re-derives these bits from the ray extents — so that its stores do not fence the window loads.)
     if (write_seen) {
         const int nx = r.x1 - r.x0 + 1, ny = r.y1 - r.y0 + 1;
         for (int i = lane; i < nx + ny; i += G) {
@@ -231,54 +313,6 @@ NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, in
             uint32_t o = *p, n = o | m;
             if (n != o) *p = (uint16_t)n;
         }
-    }
-    if (obs_row == nullptr) return;
-
-    // Step 2 (:270-275) + Steps 3-6: 16 window columns + 4 scalar quads = 20 float4 stores per env.
-    for (int j = lane; j < 20; j += G) {
-        float4 v;
-        if (j < 16) {
-            const int cx = x + (j >> 2) - 2, cy = y + (j & 3) - 2;
-            const float unknown = lut[1];
-            v.x = v.y = v.z = v.w = unknown;
-            if (cx >= 0 && cx < R.W && cy >= 0 && cy < R.D) {
-                uint32_t sw = S[s_index(R, cx, cy)];
-                if (cy == y && cx >= r.x0 && cx <= r.x1) sw |= (cx == x) ? r.zmask : zbit;
-                if (cx == x && cy >= r.y0 && cy <= r.y1) sw |= zbit;
-                const uint32_t ow = ldg(P.occz + R.occz_off + (uint32_t)(cx * R.D + cy));
-                float out[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int cz = z - 2 + k;
-                    float f = unknown;
-                    if (cz >= 0 && cz < R.H && ((sw >> cz) & 1u)) {
-                        if ((ow >> cz) & 1u) f = lut[0];                      // known wall: (-2+2)/22
-                        else {
-                            int c = (cx == x && cy == y && cz == z) ? centre_count : (int)C[c_index(R, cx, cy, cz)];
-                            f = lut[2 + imin(c, 20)];
-                        }
-                    }
-                    out[k] = f;
-                }
-                v.x = out[0]; v.y = out[1]; v.z = out[2]; v.w = out[3];
-            }
-        } else if (j == 16) {
-            v.x = sc.facing == 0 ? 1.f : 0.f; v.y = sc.facing == 1 ? 1.f : 0.f;
-            v.z = sc.facing == 2 ? 1.f : 0.f; v.w = sc.facing == 3 ? 1.f : 0.f;
-        } else if (j == 17) {
-            // float(k)/5, count/L and visited/total are f64 quotients rounded to f32 in the reference (:284-291); for
-            // integers below 2^24 that equals the correctly rounded f32 quotient (53 >= 2*24+2, Figueroa 1995).
-            v.x = fdiv_rn((float)sc.last_action, 5.0f);
-            v.y = (float)sc.was_near_wall;
-            v.z = (float)sc.last_bump;
-            v.w = fdiv_rn((float)sc.down, (float)P.L);
-        } else if (j == 18) {
-            v.x = fdiv_rn((float)sc.visited, (float)sc.total_free);
-            v.y = v.z = v.w = 0.f;
-        } else {
-            v.x = v.y = v.z = v.w = 0.f;
-        }
-        reinterpret_cast<float4 *>(obs_row)[j] = v;
     }
 }
 
@@ -335,8 +369,9 @@ NAV3D_HD void reset_env_philox(const EngineParams &P, int env, int lane, int lan
 // ---------------------------------------------------------------------------------------------------------------
 struct EpisodeRec { float episode_return; int32_t length, bumps, visited, total_free, room, terminated, truncated; };
 
-template <int G>
-NAV3D_HD void step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
+// Returns true when the env finished its episode and must be reset by the caller (auto_reset and !INLINE_RESET).
+template <int G, bool INLINE_RESET>
+NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
                        const float *lut, long long row /* row index for the output arrays */) {
     const EnvState st = P.states[env];
     const RoomDev R = P.rooms[st.room];
@@ -433,11 +468,15 @@ NAV3D_HD void step_env(const EngineParams &P, const StepIO &io, int env, int lan
             P.states[env] = ns;
         }
     }
-    if (will_reset) {
-        // every lane's reads of the old knowledge are done before any lane clears it
-        group_sync<G>(lane_in_warp);
-        reset_env_philox<G>(P, env, lane, lane_in_warp, st.episode, lut, io.obs + row * kObsDim);
+    if (INLINE_RESET) {
+        if (will_reset) {
+            // every lane's reads of the old knowledge are done before any lane clears it
+            group_sync<G>(lane_in_warp);
+            reset_env_philox<G>(P, env, lane, lane_in_warp, st.episode, lut, io.obs + row * kObsDim);
+        }
+        return false;
     }
+    return will_reset;
 }
 
 }  // namespace nav3d

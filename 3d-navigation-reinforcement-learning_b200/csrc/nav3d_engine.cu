@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -129,8 +130,16 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(EngineParams P, const int
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kBlock) step_kernel(EngineParams P, StepIO io) {
+// Pending auto-resets: the step kernel appends finished envs to a list; reset_pending_kernel (next launch on the same
+// stream) resets them.  Keeping the reset (Philox pick, knowledge clear) out of the step kernel keeps its register
+// count low, which is what its occupancy — and so its ability to hide DRAM latency — depends on.
+struct PendingResets {
+    unsigned int *count;        // [0] = entries in list, [1] = CTAs of reset_pending_kernel that have finished
+    int *list;                  // [n_envs]
+};
+
+template <int G, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) step_kernel(EngineParams P, StepIO io, PendingResets pend) {
     __shared__ float lut[24];
     fill_lut(lut);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -138,7 +147,42 @@ __global__ void __launch_bounds__(kBlock) step_kernel(EngineParams P, StepIO io)
     if (env >= P.n_envs) return;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
     const int action = (int)io.actions[env];
-    step_env<G>(P, io, (int)env, lane, liw, action, lut, env);
+    const bool need_reset = step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env) && lane == 0;
+    // warp-aggregated append
+    const unsigned active = __activemask();
+    const unsigned m = __ballot_sync(active, need_reset);
+    if (need_reset) {
+        const int leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if (liw == leader) base = atomicAdd(pend.count, (unsigned)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        pend.list[base + __popc(m & ((1u << liw) - 1u))] = (int)env;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBlock) reset_pending_kernel(EngineParams P, PendingResets pend, float *obs) {
+    __shared__ float lut[24];
+    __shared__ unsigned n_sh;
+    fill_lut(lut);
+    if (threadIdx.x == 0) n_sh = *((volatile unsigned int *)pend.count);
+    __syncthreads();
+    const unsigned n = n_sh;
+    const int lane = threadIdx.x % G, liw = threadIdx.x & 31;
+    const unsigned groups_per_block = kBlock / G;
+    for (unsigned i = blockIdx.x * groups_per_block + threadIdx.x / G; i < n; i += gridDim.x * groups_per_block) {
+        const int env = pend.list[i];
+        const uint32_t episode = P.states[env].episode;
+        group_sync<G>(liw);
+        reset_env_philox<G>(P, env, lane, liw, episode, lut, obs + (long long)env * kObsDim);
+    }
+    // the last CTA to finish clears the list for the next step
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(pend.count + 1, 1u);
+        if (done == gridDim.x - 1) { pend.count[0] = 0; pend.count[1] = 0; __threadfence(); }
+    }
 }
 
 template <int G>
@@ -164,7 +208,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(EngineParams P, int T, 
         io.reward64 = nullptr;
         io.terminated = term_scratch; io.truncated = trunc_scratch;
         io.terminal_obs = nullptr; io.episodes = nullptr;
-        step_env<G>(P, io, (int)env, lane, liw, action, lut, env);
+        step_env<G, true>(P, io, (int)env, lane, liw, action, lut, env);
         if (lane == 0) {
             if (done) done[(long long)t * N + env] = term_scratch[env] | trunc_scratch[env];
             if (actions_out) actions_out[(long long)t * N + env] = (uint8_t)action;
@@ -226,6 +270,10 @@ struct nav3d_engine {
     float *d_reward = nullptr, *d_obs = nullptr;
     uint8_t *d_term = nullptr, *d_trunc = nullptr;
     long long *d_actions = nullptr;
+    unsigned int *d_pend_count = nullptr;
+    int *d_pend_list = nullptr;
+    int minb = 0;               // __launch_bounds__ min CTAs/SM variant of the step kernel (tuning knob)
+    int reset_grid = 0;
     cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
 };
@@ -283,7 +331,7 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
         return fail(NAV3D_ERR_UNSUPPORTED, "only NAV3D_ENV_CUBIC is implemented in this build");
     if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
-    int G = cfg->lanes_per_env == 0 ? 8 : cfg->lanes_per_env;
+    int G = cfg->lanes_per_env == 0 ? 4 : cfg->lanes_per_env;
     if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
         return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
     int ndev = 0;
@@ -294,12 +342,25 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     if (!e) return fail(NAV3D_ERR_NOMEM, "out of host memory");
     e->cfg = *cfg;
     e->G = G;
+    e->minb = 8;
+    if (const char *mb = getenv("NAV3D_MINB")) e->minb = atoi(mb);
+    // Every global access of the step is a scattered 32-byte sector; the default 64-byte L2 fetch granularity would read
+    // twice the bytes from HBM (measured: profiles/step_kernel_r01_v0_details.csv).  This is a hint; failure is harmless.
+    if (!getenv("NAV3D_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        e->reset_grid = sms * 4;
+    }
     const size_t N = (size_t)cfg->n_envs;
     cudaError_t err = cudaSuccess;
     if ((err = cudaMalloc(&e->d_states, N * sizeof(EnvState))) != cudaSuccess ||
         (err = cudaMemset(e->d_states, 0, N * sizeof(EnvState))) != cudaSuccess ||
         (err = cudaMalloc(&e->d_reward, N * sizeof(float))) != cudaSuccess ||
         (err = cudaMalloc(&e->d_term, N)) != cudaSuccess || (err = cudaMalloc(&e->d_trunc, N)) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_pend_count, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (err = cudaMemset(e->d_pend_count, 0, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_pend_list, N * sizeof(int))) != cudaSuccess ||
         (err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         nav3d_destroy(e);
         return fail(NAV3D_ERR_CUDA, std::string("nav3d_create: ") + cudaGetErrorString(err));
@@ -322,7 +383,7 @@ void nav3d_destroy(nav3d_engine *e) {
     cudaSetDevice(e->cfg.device);
     free_rooms(e);
     cudaFree(e->d_states); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
-    cudaFree(e->d_obs); cudaFree(e->d_actions);
+    cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_pend_count); cudaFree(e->d_pend_list);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -475,13 +536,29 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
     io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = terminated; io.truncated = truncated;
     io.terminal_obs = terminal_obs; io.episodes = episodes;
     cudaStream_t s = (cudaStream_t)stream;
+    PendingResets pend{e->d_pend_count, e->d_pend_list};
+    const int minb = e->minb;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
-        step_kernel<G><<<grid_for(e->cfg.n_envs, G), kBlock, 0, s>>>(e->P, io);
+        const unsigned grid = grid_for(e->cfg.n_envs, G);
+        switch (minb) {
+            case 4: step_kernel<G, 4><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
+            case 6: step_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
+            case 8: step_kernel<G, 8><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
+            case 10: step_kernel<G, 10><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
+            case 12: step_kernel<G, 12><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
+            case 16: step_kernel<G, 16><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
+            default: step_kernel<G, 1><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
+        }
+        if (e->P.auto_reset) {
+            const long long max_groups = e->cfg.n_envs;
+            unsigned rgrid = (unsigned)std::min<long long>(e->reset_grid, (max_groups * G + kBlock - 1) / kBlock);
+            reset_pending_kernel<G><<<rgrid, kBlock, 0, s>>>(e->P, pend, io.obs);
+        }
         return NAV3D_OK;
     });
     if (rc) return rc;
-    e->launches++;
+    e->launches += e->P.auto_reset ? 2 : 1;
     CUDA_TRY(cudaGetLastError());
     return NAV3D_OK;
 }

@@ -89,7 +89,7 @@ void emu_step(void *h, const long long *actions, float *obs, float *reward, doub
     StepIO io;
     io.actions = actions; io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = term;
     io.truncated = trunc; io.terminal_obs = terminal_obs; io.episodes = episodes;
-    for (int env = 0; env < e->P.n_envs; env++) step_env<1>(e->P, io, env, 0, 0, (int)actions[env], e->lut, env);
+    for (int env = 0; env < e->P.n_envs; env++) step_env<1, true>(e->P, io, env, 0, 0, (int)actions[env], e->lut, env);
 }
 void emu_get_state(void *h, int *out) {
     Emu *e = (Emu *)h;
