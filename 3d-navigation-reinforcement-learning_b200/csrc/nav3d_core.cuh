@@ -111,6 +111,22 @@ template <typename T> NAV3D_HD T ldg(const T *p) {
 #endif
 }
 NAV3D_HD int imin(int a, int b) { return a < b ? a : b; }
+// Streaming (evict-first) stores for data that is written once and not read again by this engine (observations, rewards,
+// flags): keeps them from evicting the per-env knowledge lines that the NEXT step will touch again from L2.
+NAV3D_HD void store_stream(float4 *p, float4 v) {
+#ifdef __CUDA_ARCH__
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+NAV3D_HD void store_stream(float *p, float v) {
+#ifdef __CUDA_ARCH__
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 template <int G> NAV3D_HD void group_sync(int lane_in_warp) {
 #ifdef __CUDA_ARCH__
@@ -274,7 +290,7 @@ NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, in
                         }
                     }
                 }
-                reinterpret_cast<float4 *>(obs_row)[j] = make_float4(out[0], out[1], out[2], out[3]);
+                store_stream(reinterpret_cast<float4 *>(obs_row) + j, make_float4(out[0], out[1], out[2], out[3]));
             }
         }
         // Steps 3-6: the 9 scalars + zero padding = 4 more float4 (:279-307)
@@ -296,22 +312,33 @@ NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, in
             } else {
                 v.x = v.y = v.z = v.w = 0.f;
             }
-            reinterpret_cast<float4 *>(obs_row)[j] = v;
+            store_stream(reinterpret_cast<float4 *>(obs_row) + j, v);
         }
     }
 
     // Step 1 (:264-266): mark every cell the six rays examined as seen.  (Done after the gather in program order — the
     // gather re-derives these bits from the ray extents — so that its stores do not fence the window loads.)
     if (write_seen) {
-        const int nx = r.x1 - r.x0 + 1, ny = r.y1 - r.y0 + 1;
-        for (int i = lane; i < nx + ny; i += G) {
-            int cx, cy;
-            if (i < nx) { cx = r.x0 + i; cy = y; }
-            else { cx = x; cy = r.y0 + (i - nx); if (cy == y) continue; }     // centre column belongs to the x run
-            uint32_t m = (cx == x && cy == y) ? r.zmask : zbit;
-            uint16_t *p = S + s_index(R, cx, cy);
-            uint32_t o = *p, n = o | m;
-            if (n != o) *p = (uint16_t)n;
+        const int nx = r.x1 - r.x0 + 1, total = nx + (r.y1 - r.y0 + 1);
+        constexpr int RC = G >= 16 ? 2 : 4;                 // cells per lane per chunk: loads of a chunk overlap
+        for (int base = 0; base < total; base += G * RC) {
+            uint32_t idx[RC], old[RC], msk[RC];
+#pragma unroll
+            for (int q = 0; q < RC; q++) {
+                const int i = base + q * G + lane;
+                int cx = x, cy = y;
+                bool valid = i < total;
+                if (i < nx) cx = r.x0 + i;
+                else { cy = r.y0 + (i - nx); valid = valid && cy != y; }      // centre column belongs to the x run
+                msk[q] = (cx == x && cy == y) ? r.zmask : zbit;
+                idx[q] = valid ? s_index(R, cx, cy) : 0xffffffffu;
+                old[q] = valid ? (uint32_t)S[idx[q]] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < RC; q++) {
+                const uint32_t n = old[q] | msk[q];
+                if (idx[q] != 0xffffffffu && n != old[q]) S[idx[q]] = (uint16_t)n;
+            }
         }
     }
 }
@@ -448,7 +475,7 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
         if (truncated) { rew += -5.0; cents -= 500; }
         const int ret_centi = st.ret_centi + cents;
 
-        io.reward[row] = (float)rew;
+        store_stream(io.reward + row, (float)rew);
         if (io.reward64) io.reward64[row] = rew;
         io.terminated[row] = done ? 1 : 0;
         io.truncated[row] = truncated ? 1 : 0;

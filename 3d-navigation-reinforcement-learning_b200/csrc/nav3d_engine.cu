@@ -160,6 +160,20 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(EngineParams P, Step
     }
 }
 
+// Single-launch variant with the reset inlined: used for small batches, where a second (mostly idle) launch per step
+// costs more than the extra registers.
+template <int G>
+__global__ void __launch_bounds__(kBlock) step_inline_kernel(EngineParams P, StepIO io) {
+    __shared__ float lut[24];
+    fill_lut(lut);
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long env = gid / G;
+    if (env >= P.n_envs) return;
+    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
+    const int action = (int)io.actions[env];
+    step_env<G, true>(P, io, (int)env, lane, liw, action, lut, env);
+}
+
 template <int G>
 __global__ void __launch_bounds__(kBlock) reset_pending_kernel(EngineParams P, PendingResets pend, float *obs) {
     __shared__ float lut[24];
@@ -273,6 +287,7 @@ struct nav3d_engine {
     unsigned int *d_pend_count = nullptr;
     int *d_pend_list = nullptr;
     int minb = 0;               // __launch_bounds__ min CTAs/SM variant of the step kernel (tuning knob)
+    bool inline_reset = false;  // small batches: one launch per step with the reset inlined
     int reset_grid = 0;
     cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
@@ -343,6 +358,8 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     e->cfg = *cfg;
     e->G = G;
     e->minb = 8;
+    e->inline_reset = cfg->n_envs <= 32768;
+    if (const char *ir = getenv("NAV3D_INLINE_RESET")) e->inline_reset = atoi(ir) != 0;
     if (const char *mb = getenv("NAV3D_MINB")) e->minb = atoi(mb);
     // Every global access of the step is a scattered 32-byte sector; the default 64-byte L2 fetch granularity would read
     // twice the bytes from HBM (measured: profiles/step_kernel_r01_v0_details.csv).  This is a hint; failure is harmless.
@@ -541,6 +558,10 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         const unsigned grid = grid_for(e->cfg.n_envs, G);
+        if (e->inline_reset) {
+            step_inline_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
+            return NAV3D_OK;
+        }
         switch (minb) {
             case 4: step_kernel<G, 4><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
             case 6: step_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
@@ -558,7 +579,7 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
         return NAV3D_OK;
     });
     if (rc) return rc;
-    e->launches += e->P.auto_reset ? 2 : 1;
+    e->launches += (e->P.auto_reset && !e->inline_reset) ? 2 : 1;
     CUDA_TRY(cudaGetLastError());
     return NAV3D_OK;
 }

@@ -195,6 +195,37 @@ def time_steps(eng, n, steps, warmup, torch, dist, world, lanes_note=None, ring=
     return ms, ms_local, eng.launch_count - l0
 
 
+def time_steps_graph(eng, n, steps, torch, graph_len=50, ring=4, act_rows=16):
+    """Same measurement with the step launches captured in a CUDA graph (graph_len steps per replay): what a trainer that
+    graphs its rollout loop sees when the per-launch host overhead would otherwise dominate (small batches)."""
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(99)
+    actions = torch.randint(0, 6, (act_rows, n), generator=g, device=dev, dtype=torch.int64)
+    obs = torch.empty((ring, n, 80), dtype=torch.float32, device=dev)
+    rew = torch.empty(n, dtype=torch.float32, device=dev)
+    te = torch.empty(n, dtype=torch.uint8, device=dev)
+    tr = torch.empty(n, dtype=torch.uint8, device=dev)
+    eng.reset(obs[0])
+    for t in range(8):
+        eng.step(actions[t % act_rows], obs[t % ring], rew, te, tr)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.graph(graph, stream=side):
+        for t in range(graph_len):
+            eng.step(actions[t % act_rows], obs[t % ring], rew, te, tr)
+    reps = max(1, steps // graph_len)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1), reps * graph_len
+
+
 def time_e2e(eng, n, steps, torch, dist, world):
     dev = eng.device
     a = [torch.randint(0, 6, (n,), dtype=torch.int64).pin_memory() for _ in range(4)]
@@ -313,6 +344,13 @@ def main():
             extra[wl] = {"workload": s2["desc"], "value": s2["envs_total"] * k2 / (m2 / 1e3), "unit": UNIT,
                          "ms_per_step": m2 / k2, "steps": k2,
                          "roofline_frac": B_ALG[10] * s2["envs_total"] / (m2 / k2 * 1e-3) / 1e9 / peak}
+            try:
+                mg, kg = time_steps_graph(e2, s2["envs_total"], k2, torch)
+                extra[wl]["cuda_graph"] = {"value": s2["envs_total"] * kg / (mg / 1e3), "ms_per_step": mg / kg, "steps": kg,
+                                           "roofline_frac": B_ALG[10] * s2["envs_total"] / (mg / kg * 1e-3) / 1e9 / peak,
+                                           "note": "50 nav3d_step launches captured per CUDA-graph replay"}
+            except Exception as ex:  # noqa: BLE001
+                extra[wl]["cuda_graph"] = {"error": str(ex)}
             del e2
             torch.cuda.empty_cache()
         # fused random-action rollout kernel (one launch = T steps of every env), c4 size

@@ -194,3 +194,15 @@ def test_full_size_sample_against_oracle(oracle):
     free = torch.as_tensor(eng.room_free, device=eng.device)[st[:, 13].long()]
     assert bool((st[:, 4] <= free).all()) and bool((st[:, 6] == T).all()) and bool((st[:, 4] >= 1).all())
     assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("inline,minb", [("0", "8"), ("0", "12"), ("1", "8")])
+def test_both_reset_paths_and_occupancy_variants(oracle, monkeypatch, inline, minb):
+    """Auto-reset runs either inlined in the step kernel (small batches) or through the pending-reset list + second
+    kernel (large batches); both, and the register-capped kernel variants, must give the same bits."""
+    monkeypatch.setenv("NAV3D_INLINE_RESET", inline)
+    monkeypatch.setenv("NAV3D_MINB", minb)
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt"), load_room_file(ROOMS / "P2_training" / "tightcorridor.txt"),
+             load_room_file(ROOMS / "P1_training" / "Empty_room_3mx3mx3m_0.25m_cellsize.txt")]
+    n_done = lockstep(oracle, rooms, n=1500, L=10, steps=650, seed=21, lanes=4, state_every=50)
+    assert n_done > 1500
