@@ -206,3 +206,61 @@ def test_both_reset_paths_and_occupancy_variants(oracle, monkeypatch, inline, mi
              load_room_file(ROOMS / "P1_training" / "Empty_room_3mx3mx3m_0.25m_cellsize.txt")]
     n_done = lockstep(oracle, rooms, n=1500, L=10, steps=650, seed=21, lanes=4, state_every=50)
     assert n_done > 1500
+
+
+def test_scalar_facade_matches_reference_traces(cubic_traces, capsys):
+    """envs.CubicEnv.GridAgent (the drop-in for the reference's own scripts) with reset(seed=s): the room and start come
+    from CPython's `random` exactly like the reference, so the golden traces (seeded resets) replay bit-for-bit."""
+    from pathlib import Path
+
+    from envs.CubicEnv import GridAgent
+    from envs.Venv import GridAgent as VenvAgent
+    assert VenvAgent is GridAgent
+    for c in cubic_traces[:2] + cubic_traces[-2:]:
+        p = ROOMS / c["room"]
+        env = GridAgent(room_path=str(p.parent), local_map_length=c["L"], crash_penalty=c["crash_penalty"])
+        env.rooms = [Path(p)]
+        obs, info = env.reset(seed=c["seed"])
+        assert info == {} and obs.dtype == np.float32 and obs.shape == (80,)
+        assert (env.x, env.y, env.z) == tuple(c["start"]) and env.total_free_cells == c["total_free"]
+        assert np.array_equal(obs.view(np.uint32), c["obs"][0].view(np.uint32))
+        n = min(c["n"], 250) if c["policy"] == "random" else c["n"]
+        for t in range(n):
+            o, r, term, trunc, _ = env.step(int(c["actions"][t]))
+            assert isinstance(r, float) and r == c["reward"][t]
+            assert [env.x, env.y, env.z, env.facing, env.visited_count, env.bump_count, env.step_count, int(term), int(trunc)] == list(c["state"][t])
+            assert np.array_equal(o.view(np.uint32), c["obs"][t + 1].view(np.uint32))
+        assert env.get_position() == (env.x, env.y, env.z) and env.done == bool(c["state"][n - 1][7])
+        if n == c["n"]:
+            assert np.array_equal(env.internal_grid, np.minimum(c["final_ig"], 255))
+        env.close()
+    capsys.readouterr()
+
+
+def test_batched_vec_env_contract(oracle):
+    """nav3d.BatchedCubicEnv: SB3 VecEnv-shaped API (reset/step_async/step_wait, dones, terminal_observation, episode)."""
+    import torch
+    from nav3d import BatchedCubicEnv
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt")]
+    venv = BatchedCubicEnv(rooms=rooms, num_envs=64, local_map_length=10, seed=3)
+    assert venv.num_envs == 64 and venv.action_space.n == 6 and venv.observation_space.shape == (80,)
+    obs = venv.reset()
+    assert obs.shape == (64, 80) and obs.is_cuda
+    g = torch.Generator().manual_seed(0)
+    seen_done = 0
+    for t in range(200):
+        a = torch.randint(0, 6, (64,), generator=g)
+        venv.step_async(a)
+        obs, rew, dones, info = venv.step_wait()
+        assert rew.dtype == torch.float32 and dones.dtype == torch.bool
+        if bool(dones.any()):
+            infos = venv.sb3_infos(info)
+            for i in torch.nonzero(dones).flatten().tolist():
+                assert infos[i]["terminal_observation"].shape == (80,) and infos[i]["episode"]["l"] == 149
+                assert infos[i]["TimeLimit.truncated"] is True
+                seen_done += 1
+            st = venv.state().cpu().numpy()
+            assert (st[dones.cpu().numpy(), 6] == 0).all()          # auto-reset: step_count is back to 0
+    assert seen_done == 64
+    assert venv.get_attr("total_free_cells") == [149] * 64 and len(venv.env_method("get_position")) == 64
+    venv.close()
