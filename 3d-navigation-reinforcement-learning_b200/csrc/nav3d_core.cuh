@@ -67,6 +67,8 @@ struct EngineParams {
     uint32_t env_id0, seed_lo, seed_hi;
     int32_t auto_reset;
     double crash_penalty;
+    const float *dist_lut;         // simpleEnv: round(count * cell_size, 2) as f32, count = 0..L (simpleEnv.py:337)
+    int32_t obs_dim;               // 80 (CubicEnv) or 6L+7 (simpleEnv)
 };
 
 struct StepIO {                    // per-launch output pointers (any may be null except obs)
@@ -155,6 +157,20 @@ NAV3D_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     o0 = c0; o1 = c1;
+}
+NAV3D_HD void philox4x32_10_4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *o) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 NAV3D_HD uint32_t mulhi_range(uint32_t u, uint32_t n) { return (uint32_t)(((unsigned long long)u * n) >> 32); }
 
@@ -504,6 +520,213 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
         return false;
     }
     return will_reset;
+}
+
+// ===============================================================================================================
+// simpleEnv (envs/simpleEnv.py): ternary knowledge grid, ray-cell observations, goal reward
+//   step :109-150, do_action :152-186, compute_reward :189-217, get_obs :219-265, _mark_visited :273-298,
+//   _sense_direction :301-337, reset :79-107, load_room's start/goal picks :404-426.
+// Knowledge: 2 bits per cell — 00 unknown (-1), 01 seen free (0), 10 visited (1), 11 marked blocked (2) — stored per (x,y)
+// column as one u32 (low half = bit-plane 0, high half = bit-plane 1, bit z), in 4x4-column tiles of 64 B.
+// EnvState reuse: down = goal x, pad0 = goal y, pad1 = goal z.
+// ===============================================================================================================
+NAV3D_HD uint32_t k2_bytes(const RoomDev &R) { return (uint32_t)R.ntx * R.nty * 64u; }
+NAV3D_HD int k2_code(uint32_t w, int z) { return (int)(((w >> z) & 1u) | (((w >> (16 + z)) & 1u) << 1)); }
+NAV3D_HD float k2_value(int code) { return code == 0 ? -1.0f : (float)(code - 1); }
+
+struct SimpleRay { int dx, dy, dz, nfree, blocked; bool wall; };   // blocked: a 2 is appended at step nfree+1 (wall or OOB)
+
+// get_obs (simpleEnv.py:219-265) at (x,y,z): marks the knowledge and writes the 6L+7 floats.  `centre` is the centre
+// column's word as every lane holds it (after the move's visit update); the updated word is stored by lane 0.
+template <int G>
+NAV3D_HD void simple_observe(const EngineParams &P, const RoomDev &R, uint32_t *K, int lane, int lane_in_warp, int x, int y,
+                             int z, int facing, uint32_t centre_mem, uint32_t centre, int last_action, float *obs_row) {
+    const int L = P.L, W = R.W, D = R.D, H = R.H;
+    const unsigned long long wx = ldg(P.occ64 + R.occx_off + (uint32_t)(y * H + z));
+    const unsigned long long wy = ldg(P.occ64 + R.occy_off + (uint32_t)(x * H + z));
+    const unsigned long long wz = ldg(P.occz + R.occz_off + (uint32_t)(x * D + y));
+    // order :243: forward, left, right, backward, up, down.  Headings N=+y, E=+x, S=-y, W=-x.
+    const int fx = (facing == 1) - (facing == 3), fy = (facing == 0) - (facing == 2);
+    const int lf = (facing + 3) & 3, lx = (lf == 1) - (lf == 3), ly = (lf == 0) - (lf == 2);
+    SimpleRay ray[6];
+    ray[0].dx = fx; ray[0].dy = fy; ray[0].dz = 0;
+    ray[1].dx = lx; ray[1].dy = ly; ray[1].dz = 0;
+    ray[2].dx = -lx; ray[2].dy = -ly; ray[2].dz = 0;
+    ray[3].dx = -fx; ray[3].dy = -fy; ray[3].dz = 0;
+    ray[4].dx = 0; ray[4].dy = 0; ray[4].dz = 1;
+    ray[5].dx = 0; ray[5].dy = 0; ray[5].dz = -1;
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+        int ext, nfree, near, room_left;
+        if (ray[d].dx > 0) { room_left = W - 1 - x; ray_up(wx, x, imin(L, room_left), ext, nfree, near); }
+        else if (ray[d].dx < 0) { room_left = x; ray_down(wx, x, imin(L, room_left), ext, nfree, near); }
+        else if (ray[d].dy > 0) { room_left = D - 1 - y; ray_up(wy, y, imin(L, room_left), ext, nfree, near); }
+        else if (ray[d].dy < 0) { room_left = y; ray_down(wy, y, imin(L, room_left), ext, nfree, near); }
+        else if (ray[d].dz > 0) { room_left = H - 1 - z; ray_up(wz, z, imin(L, room_left), ext, nfree, near); }
+        else { room_left = z; ray_down(wz, z, imin(L, room_left), ext, nfree, near); }
+        ray[d].nfree = nfree;
+        ray[d].wall = ext > nfree;                                   // a wall stopped the ray (:321-324)
+        ray[d].blocked = ray[d].wall || (nfree == room_left && nfree < L);   // ... or the room ended (:311-319)
+    }
+    // vertical rays: all in the centre column; fold their marks into one word
+    uint32_t free_z = 0, block_z = 0;
+#pragma unroll
+    for (int d = 4; d < 6; d++) {
+        const int n = ray[d].nfree, sgn = ray[d].dz;
+        for (int s = 1; s <= n; s++) free_z |= 1u << (z + sgn * s);
+        if (ray[d].wall) block_z |= 1u << (z + sgn * (n + 1));
+        else if (ray[d].blocked && n >= 1) block_z |= 1u << (z + sgn * n);     // last in-bounds cell becomes 2 (:314-317)
+    }
+    const uint32_t lo0 = centre & 0xffffu, hi0 = centre >> 16;
+    const uint32_t lo1 = lo0 | (free_z & ~hi0 & ~lo0);                           // unknown -> seen (:327-328)
+    const uint32_t centre_seen = lo1 | (hi0 << 16);                              // what the ray cells report
+    const uint32_t centre_new = (lo1 | block_z) | ((hi0 | block_z) << 16);
+    {
+        for (int i = lane; i < 6 * L; i += G) {
+            const int d = i / L, s = i - d * L + 1;
+            const SimpleRay rd = ray[d];
+            float v = -1.0f;                                                      // padding (:334-335)
+            if (s <= rd.nfree) {
+                const int cx = x + rd.dx * s, cy = y + rd.dy * s, cz = z + rd.dz * s;
+                if (rd.dz != 0) v = k2_value(k2_code(centre_seen, cz));
+                else {
+                    uint32_t *p = K + s_index(R, cx, cy);
+                    uint32_t w = *p, n = w;
+                    int code = k2_code(w, cz);
+                    if (code == 0) { code = 1; n |= 1u << cz; }                   // -1 -> 0
+                    v = k2_value(code);
+                    if (s == rd.nfree && rd.blocked && !rd.wall) n |= (1u << cz) | (1u << (16 + cz));   // then becomes 2
+                    if (n != w) *p = n;
+                }
+            } else if (s == rd.nfree + 1 && rd.blocked) {
+                v = 2.0f;
+                if (rd.wall && rd.dz == 0) {
+                    const int cx = x + rd.dx * s, cy = y + rd.dy * s;
+                    uint32_t *p = K + s_index(R, cx, cy);
+                    uint32_t w = *p, n = w | (1u << z) | (1u << (16 + z));
+                    if (n != w) *p = n;
+                }
+            }
+            if (obs_row) obs_row[i] = v;
+        }
+    }
+    if (obs_row) {
+        for (int i = lane; i < 7; i += G)
+            obs_row[6 * L + i] = i < 6 ? ldg(P.dist_lut + ray[i].nfree) : (float)last_action;
+    }
+    if (lane == 0 && centre_new != centre_mem) K[s_index(R, x, y)] = centre_new;
+    (void)lane_in_warp;
+}
+
+template <int G>
+NAV3D_HD void simple_reset_env(const EngineParams &P, int env, int lane, int lane_in_warp, uint32_t room_idx, uint32_t k,
+                               uint32_t kg, uint32_t episode_after, float *obs_row) {
+    const RoomDev R = P.rooms[room_idx];
+    uint32_t *K = reinterpret_cast<uint32_t *>(P.know + (unsigned long long)env * P.env_stride);
+    {
+        uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *k4 = reinterpret_cast<uint4 *>(K);
+        const uint32_t n = k2_bytes(R) >> 4;
+        for (uint32_t i = lane; i < n; i += G) k4[i] = zero;
+    }
+    group_sync<G>(lane_in_warp);
+    const uint32_t cell = ldg(P.free_cells + R.free_off + k), goal = ldg(P.free_cells + R.free_off + kg);
+    const int x = cell & 0xff, y = (cell >> 8) & 0xff, z = (cell >> 16) & 0xff;
+    const uint32_t centre = 1u << (16 + z);                                       // internal_grid[start] = 1 (:85)
+    simple_observe<G>(P, R, K, lane, lane_in_warp, x, y, z, 0, 0u, centre, 0, obs_row);
+    if (lane == 0) {
+        EnvState st;
+        st.x = (uint8_t)x; st.y = (uint8_t)y; st.z = (uint8_t)z; st.facing = 0; st.last_action = 0; st.flags = 0;
+        st.down = (uint8_t)(goal & 0xff); st.pad0 = (uint8_t)((goal >> 8) & 0xff); st.pad1 = (uint16_t)((goal >> 16) & 0xff);
+        st.step_count = 0; st.visited_count = 1; st.bump_count = 0; st.ret_centi = 0;
+        st.episode = episode_after; st.room = (uint16_t)room_idx;
+        P.states[env] = st;
+    }
+}
+
+template <int G>
+NAV3D_HD void simple_reset_env_philox(const EngineParams &P, int env, int lane, int lane_in_warp, uint32_t episode,
+                                      float *obs_row) {
+    uint32_t u[4];
+    philox4x32_10_4(P.env_id0 + (uint32_t)env, episode, 0u, kStreamReset, P.seed_lo, P.seed_hi, u);
+    const uint32_t room = mulhi_range(u[0], (uint32_t)P.n_rooms);                 // random.choice(self.rooms) (:351)
+    const uint32_t nf = ldg(&P.rooms[room].n_free);
+    simple_reset_env<G>(P, env, lane, lane_in_warp, room, mulhi_range(u[1], nf), mulhi_range(u[2], nf), episode + 1u, obs_row);
+}
+
+template <int G>
+NAV3D_HD void simple_step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
+                              long long row) {
+    const EnvState st = P.states[env];
+    const RoomDev R = P.rooms[st.room];
+    uint32_t *K = reinterpret_cast<uint32_t *>(P.know + (unsigned long long)env * P.env_stride);
+    const int a = action < 0 ? 0 : (action > 5 ? 5 : action);
+    const uint32_t step_count = st.step_count + 1u;
+    const bool truncated = step_count >= R.n_free;                                 // :110-111, max_steps = total_free (:404)
+    int x = st.x, y = st.y, z = st.z, facing = st.facing;
+    int tx = x, ty = y, tz = z;
+    if (a < 4) {
+        facing = (facing + a) & 3;
+        tx += (facing == 1) - (facing == 3);
+        ty += (facing == 0) - (facing == 2);
+    } else tz += (a == 4) ? 1 : -1;
+    bool moved = false;
+    if (tx >= 0 && tx < R.W && ty >= 0 && ty < R.D && tz >= 0 && tz < R.H) {
+        const uint32_t ow = ldg(P.occz + R.occz_off + (uint32_t)(tx * R.D + ty));
+        moved = !((ow >> tz) & 1u);
+    }
+    if (moved) { x = tx; y = ty; z = tz; }
+    const uint32_t centre_mem = K[s_index(R, x, y)];
+    uint32_t centre = centre_mem;
+    group_sync<G>(lane_in_warp);                 // every lane holds the old word before lane 0 rewrites it
+    bool explored = false;
+    if (moved) {                                 // _mark_visited :286-294: 0 or -1 become 1; 1 and 2 stay
+        const int code = k2_code(centre, z);
+        if (code <= 1) { explored = true; centre = (centre & ~(1u << z)) | (1u << (16 + z)); }
+    }
+    const uint32_t visited = st.visited_count + (explored ? 1u : 0u);
+    const int gx = st.down, gy = st.pad0, gz = st.pad1;
+    bool done = (st.flags & kDone) != 0;
+    int hits = 0;
+    for (int i = 0; i < 5; i++) if (x == gx && y == gy && z - i == gz) hits++;     // :203-208
+    done = done || hits > 0;
+    const bool will_reset = P.auto_reset && (done || truncated);
+    float *orow = io.obs + row * P.obs_dim;
+    if (will_reset) orow = io.terminal_obs ? io.terminal_obs + row * P.obs_dim : nullptr;
+    if (!will_reset || orow)
+        simple_observe<G>(P, R, K, lane, lane_in_warp, x, y, z, facing, centre_mem, centre, a, orow);
+    if (lane == 0) {
+        double rew = -0.1;                                                         // compute_reward :191-215
+        int cents = -10;
+        uint32_t bump_count = st.bump_count;
+        if (!moved) { bump_count++; rew += -10.0; cents -= 1000; }
+        if (a != 2 && a < 4) { rew += 0.05; cents += 5; }                          // last_action was already set to a (:139)
+        for (int i = 0; i < hits; i++) { rew += 100.0; cents += 10000; }
+        if (explored) { rew += 1.0; cents += 100; }
+        const int ret_centi = st.ret_centi + cents;
+        store_stream(io.reward + row, (float)rew);
+        if (io.reward64) io.reward64[row] = rew;
+        io.terminated[row] = done ? 1 : 0;
+        io.truncated[row] = truncated ? 1 : 0;
+        if ((done || truncated) && io.episodes) {
+            EpisodeRec ep;
+            ep.episode_return = (float)((double)ret_centi / 100.0);
+            ep.length = (int32_t)step_count; ep.bumps = (int32_t)bump_count; ep.visited = (int32_t)visited;
+            ep.total_free = (int32_t)R.n_free; ep.room = st.room; ep.terminated = done; ep.truncated = truncated;
+            reinterpret_cast<EpisodeRec *>(io.episodes)[row] = ep;
+        }
+        if (!will_reset) {
+            EnvState ns = st;
+            ns.x = (uint8_t)x; ns.y = (uint8_t)y; ns.z = (uint8_t)z; ns.facing = (uint8_t)facing; ns.last_action = (uint8_t)a;
+            ns.flags = (uint8_t)(done ? kDone : 0u);
+            ns.step_count = step_count; ns.visited_count = visited; ns.bump_count = bump_count; ns.ret_centi = ret_centi;
+            P.states[env] = ns;
+        }
+    }
+    if (will_reset) {
+        group_sync<G>(lane_in_warp);
+        simple_reset_env_philox<G>(P, env, lane, lane_in_warp, st.episode, io.obs + row * P.obs_dim);
+    }
 }
 
 }  // namespace nav3d

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -231,6 +232,50 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(EngineParams P, int T, 
     }
 }
 
+template <int G>
+__global__ void __launch_bounds__(kBlock) simple_reset_kernel(EngineParams P, const int32_t *__restrict__ env_ids, int n,
+                                                              const int32_t *__restrict__ picks, float *obs) {
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long idx = gid / G;
+    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
+    if (idx >= n) return;
+    const int env = env_ids ? env_ids[idx] : (int)idx;
+    if (env < 0 || env >= P.n_envs) return;
+    float *orow = obs ? obs + (long long)env * P.obs_dim : nullptr;
+    const uint32_t episode = P.states[env].episode;
+    group_sync<G>(liw);
+    if (picks) {
+        uint32_t room = (uint32_t)picks[3 * idx];
+        room = room < (uint32_t)P.n_rooms ? room : (uint32_t)P.n_rooms - 1u;
+        const uint32_t nf = P.rooms[room].n_free;
+        uint32_t k = (uint32_t)picks[3 * idx + 1], kg = (uint32_t)picks[3 * idx + 2];
+        k = k < nf ? k : nf - 1u; kg = kg < nf ? kg : nf - 1u;
+        simple_reset_env<G>(P, env, lane, liw, room, k, kg, episode + 1u, orow);
+    } else {
+        simple_reset_env_philox<G>(P, env, lane, liw, episode, orow);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBlock) simple_step_kernel(EngineParams P, StepIO io) {
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long env = gid / G;
+    if (env >= P.n_envs) return;
+    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
+    simple_step_env<G>(P, io, (int)env, lane, liw, (int)io.actions[env], env);
+}
+
+__global__ void simple_get_grid_kernel(EngineParams P, int env, int16_t *out) {
+    const EnvState s = P.states[env];
+    const RoomDev R = P.rooms[s.room];
+    const int n = R.W * R.D * R.H;
+    const uint32_t *K = reinterpret_cast<const uint32_t *>(P.know + (unsigned long long)env * P.env_stride);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int z = i % R.H, y = (i / R.H) % R.D, x = i / (R.H * R.D);
+        out[i] = (int16_t)(k2_code(K[s_index(R, x, y)], z) - 1);
+    }
+}
+
 __global__ void get_state_kernel(EngineParams P, int32_t *out) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= P.n_envs) return;
@@ -241,6 +286,7 @@ __global__ void get_state_kernel(EngineParams P, int32_t *out) {
     o[7] = (s.flags & kNearWall) != 0; o[8] = (s.flags & kWasNearWall) != 0; o[9] = (s.flags & kLastBump) != 0;
     o[10] = (s.flags & kDone) != 0; o[11] = s.down; o[12] = s.last_action; o[13] = s.room;
     o[14] = (int32_t)s.episode; o[15] = s.ret_centi;
+    if (P.obs_dim != kObsDim) { o[7] = s.down; o[8] = s.pad0; o[9] = s.pad1; o[11] = 0; }   // simpleEnv: the goal cell
 }
 
 __global__ void get_grid_kernel(EngineParams P, int env, int16_t *out) {
@@ -288,6 +334,8 @@ struct nav3d_engine {
     int *d_pend_list = nullptr;
     int minb = 0;               // __launch_bounds__ min CTAs/SM variant of the step kernel (tuning knob)
     bool inline_reset = false;  // small batches: one launch per step with the reset inlined
+    bool simple = false;        // NAV3D_ENV_SIMPLE
+    float *d_dist_lut = nullptr;
     int reset_grid = 0;
     cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
@@ -342,8 +390,8 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     *out = nullptr;
     if (cfg->abi_version != NAV3D_ABI_VERSION) return fail(NAV3D_ERR_INVALID, "abi_version mismatch");
     if (cfg->n_envs <= 0) return fail(NAV3D_ERR_INVALID, "n_envs must be positive");
-    if (cfg->env_kind != NAV3D_ENV_CUBIC)
-        return fail(NAV3D_ERR_UNSUPPORTED, "only NAV3D_ENV_CUBIC is implemented in this build");
+    if (cfg->env_kind != NAV3D_ENV_CUBIC && cfg->env_kind != NAV3D_ENV_SIMPLE)
+        return fail(NAV3D_ERR_INVALID, "env_kind must be NAV3D_ENV_CUBIC or NAV3D_ENV_SIMPLE");
     if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
     int G = cfg->lanes_per_env == 0 ? 4 : cfg->lanes_per_env;
@@ -391,6 +439,21 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     P.seed_hi = (uint32_t)(cfg->seed >> 32);
     P.auto_reset = cfg->auto_reset ? 1 : 0;
     P.crash_penalty = cfg->crash_penalty;
+    e->simple = cfg->env_kind == NAV3D_ENV_SIMPLE;
+    P.obs_dim = e->simple ? 6 * cfg->local_map_length + 7 : kObsDim;
+    if (e->simple) {
+        // distances of simpleEnv: round(count * cell_size, 2) (simpleEnv.py:337) then float32
+        std::vector<float> lut((size_t)cfg->local_map_length + 1);
+        for (int c = 0; c <= cfg->local_map_length; c++)
+            lut[(size_t)c] = (float)(std::nearbyint((double)c * cfg->cell_size * 100.0) / 100.0);
+        if ((err = cudaMalloc(&e->d_dist_lut, lut.size() * sizeof(float))) != cudaSuccess ||
+            (err = cudaMemcpy(e->d_dist_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            nav3d_destroy(e);
+            return fail(NAV3D_ERR_CUDA, std::string("nav3d_create: ") + cudaGetErrorString(err));
+        }
+        P.dist_lut = e->d_dist_lut;
+        e->inline_reset = true;
+    }
     *out = e;
     return NAV3D_OK;
 }
@@ -400,7 +463,7 @@ void nav3d_destroy(nav3d_engine *e) {
     cudaSetDevice(e->cfg.device);
     free_rooms(e);
     cudaFree(e->d_states); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
-    cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_pend_count); cudaFree(e->d_pend_list);
+    cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_pend_count); cudaFree(e->d_pend_list); cudaFree(e->d_dist_lut);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -442,7 +505,8 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
 
     free_rooms(e);
     int8_t *d_dense = nullptr; uint32_t *d_off = nullptr, *d_nwall = nullptr; int32_t *d_wall = nullptr;
-    const size_t c_off = align_up(max_s, 128), stride = c_off + align_up(max_c, 128);
+    size_t c_off = align_up(max_s, 128), stride = c_off + align_up(max_c, 128);
+    if (e->simple) { c_off = 0; stride = align_up(2 * max_s, 128); }      // 2 bits per cell: 64-byte tiles
     const size_t know_bytes = stride * (size_t)e->cfg.n_envs;
     auto cleanup_tmp = [&]() { cudaFree(d_dense); cudaFree(d_off); cudaFree(d_nwall); cudaFree(d_wall); };
 #define LOAD_TRY(expr)                                                                                      \
@@ -513,7 +577,7 @@ int nav3d_room_free_cell(nav3d_engine *e, int32_t room, int32_t k, int32_t *xyz)
     return NAV3D_OK;
 }
 
-int nav3d_obs_dim(const nav3d_engine *e) { return e ? NAV3D_OBS_DIM : 0; }
+int nav3d_obs_dim(const nav3d_engine *e) { return e ? e->P.obs_dim : 0; }
 int nav3d_num_envs(const nav3d_engine *e) { return e ? e->cfg.n_envs : 0; }
 int nav3d_lanes_per_env(const nav3d_engine *e) { return e ? e->G : 0; }
 uint64_t nav3d_launch_count(const nav3d_engine *e) { return e ? e->launches : 0; }
@@ -526,12 +590,13 @@ int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_
     if (int rc = check_ready(e)) return rc;
     if (n < 0 || (!env_ids && n > e->cfg.n_envs)) return fail(NAV3D_ERR_INVALID, "n out of range");
     if (n == 0) return NAV3D_OK;
-    if (obs && ((uintptr_t)obs & 15u)) return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
+    if (obs && !e->simple && ((uintptr_t)obs & 15u)) return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
     if (int rc = set_device(e)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
-        reset_kernel<G><<<grid_for(n, G), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
+        if (e->simple) simple_reset_kernel<G><<<grid_for(n, G), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
+        else reset_kernel<G><<<grid_for(n, G), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
         return NAV3D_OK;
     });
     if (rc) return rc;
@@ -545,7 +610,7 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
     if (int rc = check_ready(e)) return rc;
     if (!actions || !obs || !reward || !terminated || !truncated)
         return fail(NAV3D_ERR_INVALID, "actions, obs, reward, terminated and truncated are required");
-    if (((uintptr_t)obs & 15u) || (terminal_obs && ((uintptr_t)terminal_obs & 15u)))
+    if (!e->simple && (((uintptr_t)obs & 15u) || (terminal_obs && ((uintptr_t)terminal_obs & 15u))))
         return fail(NAV3D_ERR_INVALID, "obs / terminal_obs must be 16-byte aligned");
     if (int rc = set_device(e)) return rc;
     StepIO io;
@@ -558,6 +623,10 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         const unsigned grid = grid_for(e->cfg.n_envs, G);
+        if (e->simple) {
+            simple_step_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
+            return NAV3D_OK;
+        }
         if (e->inline_reset) {
             step_inline_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
             return NAV3D_OK;
@@ -590,14 +659,15 @@ int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *
     if (!actions || !obs || !reward || !terminated || !truncated) return fail(NAV3D_ERR_INVALID, "NULL host buffer");
     if (int rc = set_device(e)) return rc;
     const size_t N = (size_t)e->cfg.n_envs;
-    if (!e->d_obs) CUDA_TRY(cudaMalloc(&e->d_obs, N * kObsDim * sizeof(float)));
+    const size_t obs_dim = (size_t)e->P.obs_dim;
+    if (!e->d_obs) CUDA_TRY(cudaMalloc(&e->d_obs, N * obs_dim * sizeof(float)));
     if (!e->d_actions) CUDA_TRY(cudaMalloc(&e->d_actions, N * sizeof(long long)));
     cudaStream_t s = e->own_stream;
     CUDA_TRY(cudaMemcpyAsync(e->d_actions, actions, N * sizeof(long long), cudaMemcpyHostToDevice, s));
     int rc = nav3d_step(e, reinterpret_cast<const int64_t *>(e->d_actions), e->d_obs, e->d_reward, nullptr, e->d_term,
                         e->d_trunc, nullptr, nullptr, s);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(obs, e->d_obs, N * kObsDim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(obs, e->d_obs, N * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(terminated, e->d_term, N, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(truncated, e->d_trunc, N, cudaMemcpyDeviceToHost, s));
@@ -609,6 +679,7 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
                          uint8_t *done, uint8_t *actions_out, void *stream) {
     if (int rc = check_ready(e)) return rc;
     if (T < 0) return fail(NAV3D_ERR_INVALID, "T must be >= 0");
+    if (e->simple) return fail(NAV3D_ERR_UNSUPPORTED, "nav3d_rollout_random is implemented for NAV3D_ENV_CUBIC only");
     if (T == 0) return NAV3D_OK;
     if (!obs && !obs_last) return fail(NAV3D_ERR_INVALID, "one of obs / obs_last is required");
     if ((obs && ((uintptr_t)obs & 15u)) || (obs_last && ((uintptr_t)obs_last & 15u)))
@@ -641,7 +712,8 @@ int nav3d_get_grid(nav3d_engine *e, int32_t env, int16_t *grid, void *stream) {
     if (int rc = check_ready(e)) return rc;
     if (!grid || env < 0 || env >= e->cfg.n_envs) return fail(NAV3D_ERR_INVALID, "bad env index / NULL grid");
     if (int rc = set_device(e)) return rc;
-    get_grid_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(e->P, env, grid);
+    if (e->simple) simple_get_grid_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(e->P, env, grid);
+    else get_grid_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(e->P, env, grid);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     return NAV3D_OK;

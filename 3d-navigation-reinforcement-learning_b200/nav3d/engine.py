@@ -49,7 +49,9 @@ class Engine:
         self.auto_reset = bool(auto_reset)
         self.seed = int(seed)
         self.env_id0 = int(env_id0)
-        self.obs_dim = _lib.OBS_DIM
+        self.env_kind = int(env_kind)
+        self.obs_dim = int(self._lib.nav3d_obs_dim(self._h))
+        self.pick_cols = 3 if self.env_kind == _lib.ENV_SIMPLE else 2      # simpleEnv also draws a goal cell
         self.rooms: list = []
         self.load_rooms(rooms)
 
@@ -89,8 +91,8 @@ class Engine:
 
     def reset(self, obs: Optional[torch.Tensor] = None, env_ids: Optional[torch.Tensor] = None,
               picks: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Reset all envs (``env_ids=None``) or the listed ones.  ``picks``: int32 [n,2] (room, k-th free cell) or None
-        for Philox picks.  Returns the [n_envs, obs_dim] observation tensor (only the reset rows are rewritten)."""
+        """Reset all envs (``env_ids=None``) or the listed ones.  ``picks``: int32 [n,2] (room, k-th free cell) — [n,3] with
+        the goal's free-cell index for simpleEnv — or None for Philox picks.  Returns the [n_envs, obs_dim] observation tensor (only the reset rows are rewritten)."""
         if obs is None:
             obs = self.new_obs()
         self._check(obs, torch.float32, (self.n_envs, self.obs_dim), "obs")
@@ -101,8 +103,8 @@ class Engine:
             n = self.n_envs
         if picks is not None:
             picks = picks.to(device=self.device, dtype=torch.int32).contiguous()
-            if tuple(picks.shape) != (n, 2):
-                raise ValueError(f"picks must have shape ({n}, 2)")
+            if tuple(picks.shape) != (n, self.pick_cols):
+                raise ValueError(f"picks must have shape ({n}, {self.pick_cols})")
         with torch.cuda.device(self.device):
             check(self._lib.nav3d_reset(self._h, _ptr(env_ids), n, _ptr(picks), _ptr(obs), self._stream()))
         return obs

@@ -146,3 +146,52 @@ class BatchedCubicEnv:
 
     def sb3_infos(self, info: StepInfo) -> List[dict]:
         return info.to_dicts(self._t_start)
+
+
+class BatchedSimpleEnv:
+    """N ``envs/simpleEnv.py::GridAgent`` instances on the GPU (the reference's older env variant; no driver imports it).
+
+    ``reset()`` is the reference's ``reset()`` followed by one ``get_obs()`` (the reference's own ``reset`` returns
+    ``None``, ``simpleEnv.py:79-107``).  Observations are ``6*L+7`` floats (``:233-265``)."""
+
+    def __init__(self, room_path=None, num_envs: int = 8, local_map_length: int = 4, *, rooms=None, seed: int = 0,
+                 device: int = 0, auto_reset: bool = True, env_id0: int = 0, lanes_per_env: int = 0,
+                 cell_size: float = 0.25, sort_rooms: bool = False, width: int = 20, depth: int = 20, height: int = 12):
+        from . import _lib
+        from .spaces import simple_spaces
+        if rooms is None:
+            rooms = (load_room_dir(room_path, simple=True, sort=sort_rooms) if room_path is not None
+                     else [default_box_room(width, depth, height, simple=True)])
+        self.engine = Engine(num_envs, rooms, local_map_length=local_map_length, auto_reset=auto_reset, seed=seed,
+                             env_id0=env_id0, device=device, lanes_per_env=lanes_per_env, env_kind=_lib.ENV_SIMPLE,
+                             cell_size=cell_size)
+        self.num_envs, self.device = int(num_envs), self.engine.device
+        self.action_space, self.observation_space = simple_spaces(local_map_length)
+        N, dev, d = self.num_envs, self.device, self.engine.obs_dim
+        self._obs = torch.zeros((N, d), dtype=torch.float32, device=dev)
+        self._reward = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._term = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._trunc = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._tobs = torch.zeros((N, d), dtype=torch.float32, device=dev)
+        self._eps = torch.zeros((N, 8), dtype=torch.int32, device=dev)
+        self._pending = None
+
+    def reset(self, picks=None):
+        self.engine.reset(self._obs, picks=picks)
+        return self._obs
+
+    def step_async(self, actions):
+        self._pending = torch.as_tensor(actions).to(device=self.device, dtype=torch.int64).contiguous()
+
+    def step_wait(self):
+        self.engine.step(self._pending, self._obs, self._reward, self._term, self._trunc, terminal_obs=self._tobs,
+                         episodes=self._eps)
+        self._pending = None
+        return self._obs, self._reward, (self._term | self._trunc).bool(), StepInfo(self._term, self._trunc, self._tobs, self._eps)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.engine.close()

@@ -42,6 +42,7 @@ def lib():
         "orc_philox4x32_10": (None, [P, P, P]),
         "orc_pick": (None, [C.c_uint64, C.c_uint32, C.c_uint32, I, P, P, P]),
         "orc_action": (I, [C.c_uint64, C.c_uint32, C.c_uint32]),
+        "orc_pick3": (None, [C.c_uint64, C.c_uint32, C.c_uint32, I, P, P, P, P]),
         "orc_vec_create": (P, [I, I, P, I, D, C.c_uint64, C.c_uint32, I]), "orc_vec_destroy": (None, [P]),
         "orc_vec_env": (P, [P, I]), "orc_vec_room_idx": (I, [P, I]), "orc_vec_episode": (C.c_uint32, [P, I]),
         "orc_vec_reset": (None, [P, P, P]), "orc_vec_set_ids": (None, [P, P]), "orc_vec_state": (None, [P, P]),
@@ -181,6 +182,60 @@ def pick(seed: int, env_id: int, episode: int, n_free) -> tuple:
     r, k = C.c_int(), C.c_int()
     lib().orc_pick(seed, env_id, episode, len(nf), _p(nf), C.byref(r), C.byref(k))
     return r.value, k.value
+
+
+def pick3(seed: int, env_id: int, episode: int, n_free) -> tuple:
+    nf = np.ascontiguousarray(n_free, dtype=np.int32)
+    r, k, kg = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_pick3(seed, env_id, episode, len(nf), _p(nf), C.byref(r), C.byref(k), C.byref(kg))
+    return r.value, k.value, kg.value
+
+
+class OracleSimpleVec:
+    """N simpleEnv oracles + auto-reset with Philox (room, start, goal) picks (mirrors the engine's NAV3D_ENV_SIMPLE mode:
+    reset = the reference's reset() followed by one get_obs())."""
+
+    def __init__(self, n, rooms, L=4, cell_size=0.25, seed=0, env_id0=0, auto_reset=True):
+        self.n, self.rooms, self.L, self.seed, self.env_id0, self.auto_reset = n, list(rooms), L, seed, env_id0, auto_reset
+        self.envs = [OracleSimple(L, cell_size) for _ in range(n)]
+        self.episode = [0] * n
+        self.room_idx = [0] * n
+        self.n_free = [r.n_free for r in self.rooms]
+        d = 6 * L + 7
+        self.obs = np.zeros((n, d), np.float32)
+        self.terminal_obs = np.zeros((n, d), np.float32)
+        self.reward = np.zeros(n, np.float64)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+
+    def _reset_one(self, i):
+        r, k, kg = pick3(self.seed, self.env_id0 + i, self.episode[i], self.n_free)
+        self.episode[i] += 1
+        self.room_idx[i] = r
+        room = self.rooms[r]
+        self.envs[i].reset(room, room.free_cell(k), room.free_cell(kg))
+        self.obs[i] = self.envs[i].get_obs()
+
+    def reset(self):
+        for i in range(self.n):
+            self._reset_one(i)
+        return self.obs
+
+    def step(self, actions):
+        for i in range(self.n):
+            o, r, te, tr = self.envs[i].step(int(actions[i]))
+            self.obs[i], self.reward[i], self.terminated[i], self.truncated[i] = o, r, te, tr
+            if (te or tr) and self.auto_reset:
+                self.terminal_obs[i] = o
+                self._reset_one(i)
+
+    def state(self):
+        """int64 [n, 10]: x y z facing visited bump step done room episode"""
+        out = np.zeros((self.n, 10), np.int64)
+        for i, e in enumerate(self.envs):
+            s = e.state()
+            out[i] = [s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], self.room_idx[i], self.episode[i]]
+        return out
 
 
 def action(seed: int, env_id: int, t: int) -> int:

@@ -66,3 +66,24 @@ def replay_golden_trace(c, room, make_engine):
         assert eng.reward64[0] == c["reward"][t], f"{tag} t={t}: reward {eng.reward64[0]} want {c['reward'][t]}"
         assert eng.reward[0] == np.float32(c["reward"][t]), f"{tag} t={t}: f32 reward"
     assert np.array_equal(eng.grid(0), np.minimum(c["final_ig"], 255).astype(np.int16)), f"{tag}: final knowledge grid"
+
+
+def replay_simple_golden_trace(c, room, make_engine):
+    """Replays one simpleEnv reference trace (tests/golden/simple_traces.npz): reset with injected (room, start, goal),
+    the reference's `reset(); get_obs()` then n steps.  `make_engine(rooms, L)` returns an engine-like object."""
+    fc = room.free_cells()
+    k = int(np.nonzero((fc == np.asarray(c["start"])).all(axis=1))[0][0])
+    kg = int(np.nonzero((fc == np.asarray(c["goal"])).all(axis=1))[0][0])
+    eng = make_engine([room], c["L"])
+    obs0 = np.array(eng.reset(picks=np.array([[0, k, kg]], dtype=np.int32)))
+    tag = f"simple {c['room']} L={c['L']}"
+    assert np.array_equal(obs0[0].view(np.uint32), c["obs"][0].view(np.uint32)), f"{tag}: reset obs {obs0[0]} vs {c['obs'][0]}"
+    for t in range(c["n"]):
+        eng.step(np.array([c["actions"][t]], dtype=np.int64))
+        s = eng.state()[0]
+        got = [s[0], s[1], s[2], s[3], s[4], s[5], s[6], int(eng.term[0]), int(eng.trunc[0])]
+        assert got == list(c["state"][t]), f"{tag} t={t}: state {got} want {list(c['state'][t])}"
+        assert np.array_equal(eng.obs[0].view(np.uint32), c["obs"][t + 1].view(np.uint32)), \
+            f"{tag} t={t}: obs {eng.obs[0]} want {c['obs'][t + 1]}"
+        assert eng.reward64[0] == c["reward"][t], f"{tag} t={t}: reward {eng.reward64[0]} want {c['reward'][t]}"
+    assert np.array_equal(eng.grid(0), c["final_ig"].astype(np.int16)), f"{tag}: final knowledge grid"

@@ -69,3 +69,14 @@ def test_emu_replays_reference_golden_traces(cubic_traces):
         replay_golden_trace(c, room, lambda rooms, L, crash, ar: EmuEngine(1, rooms, L, crash, 0, 0, ar))
         n_term += int(c["state"][:, 7].max())
     assert n_term >= 2      # the coverage-policy traces reach the 84 % termination branch
+
+
+def test_emu_simple_env_replays_reference_golden_traces(simple_traces):
+    from emu_harness import EmuEngine
+    from lockstep import replay_simple_golden_trace
+    n_term = 0
+    for c in simple_traces:
+        room = load_room_file(ROOMS / c["room"], simple=True)
+        replay_simple_golden_trace(c, room, lambda rooms, L: EmuEngine(1, rooms, L, -2.0, 0, 0, False, simple=True))
+        n_term += int(c["state"][:, 7].max())
+    assert n_term >= 1
