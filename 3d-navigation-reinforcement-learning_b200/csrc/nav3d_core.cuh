@@ -466,7 +466,10 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
         ObsScalars sc;
         sc.facing = facing; sc.last_action = st.last_action; sc.was_near_wall = (flags & kWasNearWall) != 0;
         sc.last_bump = (flags & kLastBump) != 0; sc.down = r.down; sc.visited = visited; sc.total_free = R.n_free;
-        observe<G>(P, R, envk, lane, x, y, z, r, c_new, !will_reset, sc, lut, orow);
+        // The cells a ray pass marks depend only on the position (L and the room are fixed), and marks are never erased
+        // within an episode: every earlier stay at this cell (c_old >= 1, which includes every bump) already marked
+        // them.  Only a FIRST visit has anything to write, so revisits skip the ray marking and its scattered traffic.
+        observe<G>(P, R, envk, lane, x, y, z, r, c_new, !will_reset && explored, sc, lut, orow);
         if (r.near_wall) flags |= kNearWall;
     } else { r.down = 0; }
 

@@ -394,7 +394,10 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
         return fail(NAV3D_ERR_INVALID, "env_kind must be NAV3D_ENV_CUBIC or NAV3D_ENV_SIMPLE");
     if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
-    int G = cfg->lanes_per_env == 0 ? 4 : cfg->lanes_per_env;
+    // Defaults from the sweep in DESIGN.md §6: huge batches are bound by scattered HBM traffic and want the fewest redundant
+    // lanes that still keep stores sector-wide (G = 2, 80 registers); smaller, L2-resident batches prefer G = 4 at 64.
+    const bool huge = cfg->n_envs >= (1 << 18);
+    int G = cfg->lanes_per_env == 0 ? (huge ? 2 : 4) : cfg->lanes_per_env;
     if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
         return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
     int ndev = 0;
@@ -405,7 +408,7 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     if (!e) return fail(NAV3D_ERR_NOMEM, "out of host memory");
     e->cfg = *cfg;
     e->G = G;
-    e->minb = 8;
+    e->minb = (G <= 2) ? 6 : 8;
     e->inline_reset = cfg->n_envs <= 32768;
     if (const char *ir = getenv("NAV3D_INLINE_RESET")) e->inline_reset = atoi(ir) != 0;
     if (const char *mb = getenv("NAV3D_MINB")) e->minb = atoi(mb);
