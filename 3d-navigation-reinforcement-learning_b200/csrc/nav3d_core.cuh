@@ -243,6 +243,21 @@ struct ObsScalars {
     uint32_t visited, total_free;
 };
 
+// 4 bits -> 4 byte masks (bit k -> byte k = 0xFF)
+NAV3D_HD uint32_t expand4(uint32_t b) {
+    const uint32_t m = (b * 0x00204081u) & 0x01010101u;      // the four partial products land on distinct bits: no carries
+    return (m << 8) - m;
+}
+NAV3D_HD uint32_t vminu4_20(uint32_t v) {                    // per-byte min(v, 20)
+#ifdef __CUDA_ARCH__
+    return __vminu4(v, 0x14141414u);
+#else
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) { uint32_t b = (v >> (8 * k)) & 0xffu; r |= (b < 20u ? b : 20u) << (8 * k); }
+    return r;
+#endif
+}
+
 template <int G>
 NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z,
                       const Rays &r, int centre_count, bool write_seen, const ObsScalars &sc, const float *lut,
@@ -252,61 +267,89 @@ NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, in
     const uint32_t zbit = 1u << z;
 
     if (obs_row != nullptr) {
-        // Step 2 (:270-275): the 4x4x4 window, one (x,y) column = one float4 of the observation.  All loads of a batch
-        // of columns are issued before any of them is used so that they overlap (memory-level parallelism).
-        constexpr int CPL = (16 + G - 1) / G;          // window columns per lane
-        constexpr int CH = CPL > 4 ? 4 : CPL;          // columns per batch
-        const int zb0 = (z - 2) >> 1;                  // first z-brick of the window (may be -1)
-        const int zsh = ((z - 2) - 2 * zb0) * 8;       // bit offset of cell z-2 inside the 3-brick column word (0 or 8)
+        // Step 2 (:270-275): the 4x4x4 window; one (x,y) column = 4 cells = one float4 of the observation.
+        // Lane -> columns: column j = 4*dxi + dyi with dyi = (lane & 3) + b*G (b < NY) and dxi = (lane >> 2) + a*XS (a < NX),
+        // so the x-dependent and y-dependent halves of every index (they are separable, see s_index / c_index) are
+        // computed once per a / per b instead of once per column.
+        constexpr int NY = G >= 4 ? 1 : 4 / G;               // distinct dy per lane
+        constexpr int NX = G >= 16 ? 1 : (16 / G) / NY;      // distinct dx per lane
+        constexpr int XS = G >= 4 ? G / 4 : 1;               // stride of dxi between a-iterations
+        constexpr int AB = (4 / NY) < NX ? (4 / NY) : NX;    // a-iterations per batch (about 4 columns in flight)
+        const int nbz32 = R.nbz * 32, ntx16 = R.ntx * 16, cys = R.ntx * nbz32;
+        const int zb0 = (z - 2) >> 1;                        // first z-brick of the window (may be -1)
+        const int zsh = ((z - 2) - 2 * zb0) * 8;             // bit offset of cell z-2 inside the 3-brick column word (0 or 8)
+        const uint32_t zvalid = ((((1u << R.H) - 1u) << 2) >> z) & 15u;    // window cells inside [0, H)
+        const bool b0 = zb0 >= 0, b1 = zb0 + 1 < R.nbz, b2 = zsh != 0 && zb0 + 2 < R.nbz;
+        const int zoff = zb0 * 32;
         const float unknown = lut[1];
+        // y halves
+        int ys[NY], yc[NY], cyv[NY];
+        bool yin[NY], yray[NY];
 #pragma unroll
-        for (int q0 = 0; q0 < CPL; q0 += CH) {
-            uint32_t sw[CH], ow[CH];
-            unsigned long long cw[CH];
-            bool inb[CH];
+        for (int b = 0; b < NY; b++) {
+            const int cy = y + (lane & 3) + b * G - 2;
+            cyv[b] = cy;
+            yin[b] = cy >= 0 && cy < R.D;
+            yray[b] = cy >= r.y0 && cy <= r.y1;
+            ys[b] = (cy >> 2) * ntx16 + (cy & 3);
+            yc[b] = (cy >> 2) * cys + ((cy & 3) << 1) + zoff;
+        }
 #pragma unroll
-            for (int q = 0; q < CH; q++) {
-                const int j = lane + (q0 + q) * G;
-                const int cx = x + (j >> 2) - 2, cy = y + (j & 3) - 2;
-                inb[q] = j < 16 && cx >= 0 && cx < R.W && cy >= 0 && cy < R.D;
-                sw[q] = 0; ow[q] = 0; cw[q] = 0;
-                if (inb[q]) {
-                    sw[q] = S[s_index(R, cx, cy)];
-                    ow[q] = ldg(P.occz + R.occz_off + (uint32_t)(cx * R.D + cy));
-                    const uint16_t *cp = reinterpret_cast<const uint16_t *>(C + c_index(R, cx, cy, 0));   // brick 0 of the column
-                    unsigned long long w = 0;
-                    if (zb0 >= 0) w = cp[zb0 * 16];                                          // bricks are 32 B = 16 u16 apart
-                    if (zb0 + 1 < R.nbz) w |= (unsigned long long)cp[(zb0 + 1) * 16] << 16;
-                    if (zsh && zb0 + 2 < R.nbz) w |= (unsigned long long)cp[(zb0 + 2) * 16] << 32;
-                    cw[q] = w;
+        for (int a0 = 0; a0 < NX; a0 += AB) {
+            uint32_t sw[AB][NY], ow[AB][NY];
+            unsigned long long cw[AB][NY];
+            bool inb[AB][NY];
+#pragma unroll
+            for (int a = 0; a < AB; a++) {
+                const int dxi = (lane >> 2) + (a0 + a) * XS;
+                const int cx = x + dxi - 2;
+                const bool xin = dxi < 4 && cx >= 0 && cx < R.W;
+                const int xs = ((cx >> 2) << 4) + ((cx & 3) << 2);
+                const int xc = (cx >> 2) * nbz32 + ((cx & 3) << 3);
+                const int xo = cx * R.D;
+#pragma unroll
+                for (int b = 0; b < NY; b++) {
+                    inb[a][b] = xin && yin[b];
+                    sw[a][b] = 0; ow[a][b] = 0; cw[a][b] = 0;
+                    if (inb[a][b]) {
+                        sw[a][b] = S[xs + ys[b]];
+                        ow[a][b] = ldg(P.occz + R.occz_off + (uint32_t)(xo + cyv[b]));
+                        const uint16_t *cp = reinterpret_cast<const uint16_t *>(C + (xc + yc[b]));   // brick zb0 of the column
+                        unsigned long long w = 0;
+                        if (b0) w = cp[0];                                   // bricks are 32 B = 16 u16 apart
+                        if (b1) w |= (unsigned long long)cp[16] << 16;
+                        if (b2) w |= (unsigned long long)cp[32] << 32;
+                        cw[a][b] = w;
+                    }
                 }
             }
 #pragma unroll
-            for (int q = 0; q < CH; q++) {
-                const int j = lane + (q0 + q) * G;
-                if (j >= 16) continue;
-                const int cx = x + (j >> 2) - 2, cy = y + (j & 3) - 2;
-                float out[4];
-                out[0] = out[1] = out[2] = out[3] = unknown;
-                if (inb[q]) {
-                    uint32_t s = sw[q];
-                    if (cy == y && cx >= r.x0 && cx <= r.x1) s |= (cx == x) ? r.zmask : zbit;
-                    if (cx == x && cy >= r.y0 && cy <= r.y1) s |= zbit;
-                    const bool centre_col = (cx == x && cy == y);
+            for (int a = 0; a < AB; a++) {
+                const int dxi = (lane >> 2) + (a0 + a) * XS;
+                if (dxi >= 4) continue;
+                const int cx = x + dxi - 2;
+                const bool xray = cx >= r.x0 && cx <= r.x1;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int cz = z - 2 + k;
-                        if (cz >= 0 && cz < R.H && ((s >> cz) & 1u)) {
-                            if ((ow[q] >> cz) & 1u) out[k] = lut[0];               // known wall: (-2+2)/22
-                            else {
-                                int c = (int)((cw[q] >> (zsh + 8 * k)) & 0xffu);
-                                if (centre_col && k == 2) c = centre_count;
-                                out[k] = lut[2 + imin(c, 20)];
-                            }
-                        }
+                for (int b = 0; b < NY; b++) {
+                    const int cy = cyv[b];
+                    float4 v = make_float4(unknown, unknown, unknown, unknown);
+                    if (inb[a][b]) {
+                        uint32_t sbits = sw[a][b];
+                        const bool centre_col = (cx == x && cy == y);
+                        if (cy == y && xray) sbits |= centre_col ? r.zmask : zbit;
+                        if (cx == x && yray[b]) sbits |= zbit;
+                        uint32_t c4 = (uint32_t)(cw[a][b] >> zsh);          // byte k = counter of cell z-2+k
+                        if (centre_col) c4 = (c4 & 0xff00ffffu) | ((uint32_t)centre_count << 16);
+                        c4 = vminu4_20(c4) + 0x02020202u;                    // clip at 20 (:273-274), +2 = LUT index of a free cell
+                        const uint32_t s4 = ((sbits << 2) >> z) & zvalid;    // seen, in range
+                        const uint32_t w4 = ((ow[a][b] << 2) >> z) & s4;     // ... and a wall
+                        const uint32_t seen = expand4(s4), wall = expand4(w4);
+                        const uint32_t idx = (c4 & seen & ~wall) | (0x01010101u & ~seen);   // unknown -> 1, known wall -> 0
+                        v.x = lut[idx & 0xffu]; v.y = lut[(idx >> 8) & 0xffu];
+                        v.z = lut[(idx >> 16) & 0xffu]; v.w = lut[idx >> 24];
                     }
+                    store_stream(reinterpret_cast<float4 *>(obs_row) + (dxi * 4 + (cy - y + 2)), v);
                 }
-                store_stream(reinterpret_cast<float4 *>(obs_row) + j, make_float4(out[0], out[1], out[2], out[3]));
             }
         }
         // Steps 3-6: the 9 scalars + zero padding = 4 more float4 (:279-307)

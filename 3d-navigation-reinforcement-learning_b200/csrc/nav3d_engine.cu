@@ -161,6 +161,30 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(EngineParams P, Step
     }
 }
 
+// Out-of-line reset for the single-launch step kernel: called at the very end of a step, when almost nothing is live, so
+// the kernel's register count stays that of the step itself.
+template <int G>
+__device__ __noinline__ void reset_out_of_line(const EngineParams &P, int env, int lane, int liw, uint32_t episode,
+                                               const float *lut, float *obs_row) {
+    reset_env_philox<G>(P, env, lane, liw, episode, lut, obs_row);
+}
+
+template <int G, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_constant__ EngineParams P, StepIO io) {
+    __shared__ float lut[24];
+    fill_lut(lut);
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long env = gid / G;
+    if (env >= P.n_envs) return;
+    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
+    const int action = (int)io.actions[env];
+    if (step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env)) {
+        const uint32_t episode = P.states[env].episode;       // untouched by a step that ends its episode
+        group_sync<G>(liw);                                    // all lanes are done reading the old knowledge
+        reset_out_of_line<G>(P, (int)env, lane, liw, episode, lut, io.obs + env * kObsDim);
+    }
+}
+
 // Single-launch variant with the reset inlined: used for small batches, where a second (mostly idle) launch per step
 // costs more than the extra registers.
 template <int G>
@@ -334,6 +358,7 @@ struct nav3d_engine {
     int *d_pend_list = nullptr;
     int minb = 0;               // __launch_bounds__ min CTAs/SM variant of the step kernel (tuning knob)
     bool inline_reset = false;  // small batches: one launch per step with the reset inlined
+    int reset_mode = 0;         // 0 pending list + second kernel, 1 inlined, 2 out-of-line call in the same kernel
     bool simple = false;        // NAV3D_ENV_SIMPLE
     float *d_dist_lut = nullptr;
     int reset_grid = 0;
@@ -394,10 +419,8 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
         return fail(NAV3D_ERR_INVALID, "env_kind must be NAV3D_ENV_CUBIC or NAV3D_ENV_SIMPLE");
     if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
-    // Defaults from the sweep in DESIGN.md §6: huge batches are bound by scattered HBM traffic and want the fewest redundant
-    // lanes that still keep stores sector-wide (G = 2, 80 registers); smaller, L2-resident batches prefer G = 4 at 64.
-    const bool huge = cfg->n_envs >= (1 << 18);
-    int G = cfg->lanes_per_env == 0 ? (huge ? 2 : 4) : cfg->lanes_per_env;
+    // Default from the sweeps in DESIGN.md §6: 4 lanes per env at 64 registers (__launch_bounds__(128, 8)).
+    int G = cfg->lanes_per_env == 0 ? 4 : cfg->lanes_per_env;
     if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
         return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
     int ndev = 0;
@@ -408,9 +431,12 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     if (!e) return fail(NAV3D_ERR_NOMEM, "out of host memory");
     e->cfg = *cfg;
     e->G = G;
-    e->minb = (G <= 2) ? 6 : 8;
-    e->inline_reset = cfg->n_envs <= 32768;
-    if (const char *ir = getenv("NAV3D_INLINE_RESET")) e->inline_reset = atoi(ir) != 0;
+    e->minb = 8;
+    // reset_mode 2 (one launch per step, reset as an out-of-line call) is the default; 0 = pending list + second kernel,
+    // 1 = reset inlined (more registers).  NAV3D_INLINE_RESET selects another mode for experiments and tests.
+    e->inline_reset = true;
+    e->reset_mode = 2;
+    if (const char *ir = getenv("NAV3D_INLINE_RESET")) { e->reset_mode = atoi(ir); e->inline_reset = e->reset_mode != 0; }
     if (const char *mb = getenv("NAV3D_MINB")) e->minb = atoi(mb);
     // Every global access of the step is a scattered 32-byte sector; the default 64-byte L2 fetch granularity would read
     // twice the bytes from HBM (measured: profiles/step_kernel_r01_v0_details.csv).  This is a hint; failure is harmless.
@@ -631,7 +657,13 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
             return NAV3D_OK;
         }
         if (e->inline_reset) {
-            step_inline_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
+            if (e->reset_mode == 2) {
+                switch (minb) {
+                    case 6: step_call_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io); break;
+                    case 10: step_call_kernel<G, 10><<<grid, kBlock, 0, s>>>(e->P, io); break;
+                    default: step_call_kernel<G, 8><<<grid, kBlock, 0, s>>>(e->P, io); break;
+                }
+            } else step_inline_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
             return NAV3D_OK;
         }
         switch (minb) {

@@ -196,10 +196,10 @@ def test_full_size_sample_against_oracle(oracle):
     assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
 
 
-@pytest.mark.parametrize("inline,minb", [("0", "8"), ("0", "12"), ("1", "8")])
+@pytest.mark.parametrize("inline,minb", [("0", "8"), ("0", "12"), ("1", "8"), ("2", "8"), ("2", "10")])
 def test_both_reset_paths_and_occupancy_variants(oracle, monkeypatch, inline, minb):
-    """Auto-reset runs either inlined in the step kernel (small batches) or through the pending-reset list + second
-    kernel (large batches); both, and the register-capped kernel variants, must give the same bits."""
+    """Auto-reset has three implementations — out-of-line call in the step kernel (default, mode 2), inlined (1), pending
+    list + second kernel (0); all of them, and the register-capped kernel variants, must give the same bits."""
     monkeypatch.setenv("NAV3D_INLINE_RESET", inline)
     monkeypatch.setenv("NAV3D_MINB", minb)
     rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt"), load_room_file(ROOMS / "P2_training" / "tightcorridor.txt"),
