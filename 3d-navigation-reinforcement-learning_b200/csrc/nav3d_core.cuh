@@ -194,6 +194,8 @@ struct Rays {
     uint32_t zmask;            // bits of the centre column touched by the +-z rays (centre bit included)
     int near_wall;             // a wall at distance 1 in any direction (:378-379)
     int down;                  // free cells seen below (:394-395)
+    uint32_t blocked6;         // bit d set: a move in direction d bumps (wall or room edge at distance 1);
+                               // d = 0 +x, 1 -x, 2 +y, 3 -y, 4 +z, 5 -z.  Cached in the record for the next step's move.
 };
 
 // cells p+1 .. p+n along increasing bit index of w
@@ -221,17 +223,19 @@ NAV3D_HD Rays cast_rays(const EngineParams &P, const RoomDev &R, int x, int y, i
     unsigned long long wy = ldg(P.occ64 + R.occy_off + (uint32_t)(x * H + z));
     unsigned long long wz = ldg(P.occz + R.occz_off + (uint32_t)(x * D + y));
     Rays r;
-    int ext, nfree, near, any = 0;
-    ray_up(wx, x, imin(L, W - 1 - x), ext, nfree, near);   r.x1 = x + ext; any |= near;
-    ray_down(wx, x, imin(L, x), ext, nfree, near);         r.x0 = x - ext; any |= near;
-    ray_up(wy, y, imin(L, D - 1 - y), ext, nfree, near);   r.y1 = y + ext; any |= near;
-    ray_down(wy, y, imin(L, y), ext, nfree, near);         r.y0 = y - ext; any |= near;
+    int ext, nfree, near, any = 0, n;
+    uint32_t blk = 0;
+    n = imin(L, W - 1 - x); ray_up(wx, x, n, ext, nfree, near);   r.x1 = x + ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 0;
+    n = imin(L, x);         ray_down(wx, x, n, ext, nfree, near); r.x0 = x - ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 1;
+    n = imin(L, D - 1 - y); ray_up(wy, y, n, ext, nfree, near);   r.y1 = y + ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 2;
+    n = imin(L, y);         ray_down(wy, y, n, ext, nfree, near); r.y0 = y - ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 3;
     int zu, zd;
-    ray_up(wz, z, imin(L, H - 1 - z), zu, nfree, near);    any |= near;
-    ray_down(wz, z, imin(L, z), zd, nfree, near);          any |= near;
+    n = imin(L, H - 1 - z); ray_up(wz, z, n, zu, nfree, near);    any |= near; blk |= (uint32_t)(near | (n <= 0)) << 4;
+    n = imin(L, z);         ray_down(wz, z, n, zd, nfree, near);  any |= near; blk |= (uint32_t)(near | (n <= 0)) << 5;
     r.down = nfree;
     r.zmask = ((2u << (z + zu)) - 1u) & ~((1u << (z - zd)) - 1u);
     r.near_wall = any;
+    r.blocked6 = blk;
     return r;
 }
 
@@ -258,148 +262,180 @@ NAV3D_HD uint32_t vminu4_20(uint32_t v) {                    // per-byte min(v, 
 #endif
 }
 
+// Lane -> window columns.  Column j = 4*dxi + dyi of the 4x4 (x,y) window, dyi = (lane & 3) + b*G (b < NY),
+// dxi = (lane >> 2) + a*XS (a < NX); a batch is AB a-iterations (about four columns whose loads are in flight together).
+template <int G> struct WinMap {
+    static constexpr int NY = G >= 4 ? 1 : 4 / G;
+    static constexpr int NX = G >= 16 ? 1 : (16 / G) / NY;
+    static constexpr int XS = G >= 4 ? G / 4 : 1;
+    static constexpr int AB = (4 / NY) < NX ? (4 / NY) : NX;
+};
+template <int G> struct WinBatch {                 // what one batch of window loads leaves in registers
+    uint32_t sw[WinMap<G>::AB][WinMap<G>::NY];     // S word of the column
+    uint32_t ow[WinMap<G>::AB][WinMap<G>::NY];     // occupancy word of the column
+    unsigned long long cw[WinMap<G>::AB][WinMap<G>::NY];   // counters of the column for z-bricks zb0 .. zb0+2
+    bool inb[WinMap<G>::AB][WinMap<G>::NY];
+};
+
+// Issue the loads of one batch (Step 2 of get_obs, :270).  Every index splits into an x half and a y half (see s_index /
+// c_index), computed once per a / per b.
+template <int G>
+NAV3D_HD void window_load(const EngineParams &P, const RoomDev &R, const uint8_t *envk, int lane, int x, int y, int z,
+                          int a0, WinBatch<G> &wb) {
+    using M = WinMap<G>;
+    const uint16_t *__restrict__ S = reinterpret_cast<const uint16_t *>(envk);
+    const uint8_t *__restrict__ C = envk + P.c_off;
+    const int nbz32 = R.nbz * 32, ntx16 = R.ntx * 16, cys = R.ntx * nbz32;
+    const int zb0 = (z - 2) >> 1;                        // first z-brick of the window (may be -1)
+    const bool odd = ((z - 2) & 1) != 0;
+    const bool b0 = zb0 >= 0, b1 = zb0 + 1 < R.nbz, b2 = odd && zb0 + 2 < R.nbz;
+    const int zoff = zb0 * 32;
+#pragma unroll
+    for (int a = 0; a < M::AB; a++) {
+        const int dxi = (lane >> 2) + (a0 + a) * M::XS;
+        const int cx = x + dxi - 2;
+        const bool xin = dxi < 4 && cx >= 0 && cx < R.W;
+        const int xs = ((cx >> 2) << 4) + ((cx & 3) << 2);
+        const int xc = (cx >> 2) * nbz32 + ((cx & 3) << 3) + zoff;
+        const int xo = cx * R.D;
+#pragma unroll
+        for (int b = 0; b < M::NY; b++) {
+            const int cy = y + (lane & 3) + b * G - 2;
+            const bool in = xin && cy >= 0 && cy < R.D;
+            wb.inb[a][b] = in;
+            wb.sw[a][b] = 0; wb.ow[a][b] = 0; wb.cw[a][b] = 0;
+            if (in) {
+                wb.sw[a][b] = S[xs + (cy >> 2) * ntx16 + (cy & 3)];
+                wb.ow[a][b] = ldg(P.occz + R.occz_off + (uint32_t)(xo + cy));
+                const uint16_t *cp = reinterpret_cast<const uint16_t *>(C + (xc + (cy >> 2) * cys + ((cy & 3) << 1)));
+                unsigned long long w = 0;                              // bricks are 32 B = 16 u16 apart
+                if (b0) w = cp[0];
+                if (b1) w |= (unsigned long long)cp[16] << 16;
+                if (b2) w |= (unsigned long long)cp[32] << 32;
+                wb.cw[a][b] = w;
+            }
+        }
+    }
+}
+
+// Turn one batch into observation floats: clip to [-2, 20], (m + 2) / 22 (:273-275), one float4 per column.
+template <int G>
+NAV3D_HD void window_store(const RoomDev &R, int lane, int x, int y, int z, int a0, const WinBatch<G> &wb, const Rays &r,
+                           int centre_count, const float *lut, float *__restrict__ obs_row) {
+    using M = WinMap<G>;
+    const uint32_t zbit = 1u << z;
+    const int zsh = ((z - 2) & 1) * 8;                   // bit offset of cell z-2 inside the column word
+    const uint32_t zvalid = ((((1u << R.H) - 1u) << 2) >> z) & 15u;    // window cells inside [0, H)
+    const float unknown = lut[1];
+#pragma unroll
+    for (int a = 0; a < M::AB; a++) {
+        const int dxi = (lane >> 2) + (a0 + a) * M::XS;
+        if (dxi >= 4) continue;
+        const int cx = x + dxi - 2;
+        const bool xray = cx >= r.x0 && cx <= r.x1;
+#pragma unroll
+        for (int b = 0; b < M::NY; b++) {
+            const int dyi = (lane & 3) + b * G, cy = y + dyi - 2;
+            float4 v = make_float4(unknown, unknown, unknown, unknown);
+            if (wb.inb[a][b]) {
+                uint32_t sbits = wb.sw[a][b];
+                const bool centre_col = (dxi == 2 && dyi == 2);
+                // the cells this step's rays see (they may not be in memory yet: marking happens after the gather)
+                if (dyi == 2 && xray) sbits |= centre_col ? r.zmask : zbit;
+                if (dxi == 2 && cy >= r.y0 && cy <= r.y1) sbits |= zbit;
+                uint32_t c4 = (uint32_t)(wb.cw[a][b] >> zsh);                    // byte k = counter of cell z-2+k
+                if (centre_col) c4 = (c4 & 0xff00ffffu) | ((uint32_t)centre_count << 16);
+                c4 = vminu4_20(c4) + 0x02020202u;                               // clip at 20, +2 = LUT index of a free cell
+                const uint32_t s4 = ((sbits << 2) >> z) & zvalid;               // seen, in range
+                const uint32_t w4 = ((wb.ow[a][b] << 2) >> z) & s4;             // ... and a wall
+                const uint32_t seen = expand4(s4), wall = expand4(w4);
+                const uint32_t idx = (c4 & seen & ~wall) | (0x01010101u & ~seen);   // unknown -> 1, known wall -> 0
+                v.x = lut[idx & 0xffu]; v.y = lut[(idx >> 8) & 0xffu];
+                v.z = lut[(idx >> 16) & 0xffu]; v.w = lut[idx >> 24];
+            }
+            store_stream(reinterpret_cast<float4 *>(obs_row) + (dxi * 4 + dyi), v);
+        }
+    }
+}
+
+// Steps 3-6 of get_obs: the 9 scalars + zero padding = 4 more float4 (:279-307)
+template <int G>
+NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &sc, float *__restrict__ obs_row) {
+    for (int j = 16 + lane; j < 20; j += G) {
+        float4 v;
+        if (j == 16) {
+            v.x = sc.facing == 0 ? 1.f : 0.f; v.y = sc.facing == 1 ? 1.f : 0.f;
+            v.z = sc.facing == 2 ? 1.f : 0.f; v.w = sc.facing == 3 ? 1.f : 0.f;
+        } else if (j == 17) {
+            // float(k)/5, count/L and visited/total are f64 quotients rounded to f32 in the reference (:284-291); for
+            // integers below 2^24 that equals the correctly rounded f32 quotient (53 >= 2*24+2, Figueroa 1995).
+            v.x = fdiv_rn((float)sc.last_action, 5.0f);
+            v.y = (float)sc.was_near_wall;
+            v.z = (float)sc.last_bump;
+            v.w = fdiv_rn((float)sc.down, (float)P.L);
+        } else if (j == 18) {
+            v.x = fdiv_rn((float)sc.visited, (float)sc.total_free);
+            v.y = v.z = v.w = 0.f;
+        } else {
+            v.x = v.y = v.z = v.w = 0.f;
+        }
+        store_stream(reinterpret_cast<float4 *>(obs_row) + j, v);
+    }
+}
+
+// Step 1 of get_obs (:264-266): mark every cell the six rays examined as seen.  Runs after the gather in program order
+// (the gather re-derives these bits from the ray extents) so that its stores do not fence the window loads.  The x run
+// (centre column included, which also takes the +-z cells) and the y run are handled as one index space.
+template <int G>
+NAV3D_HD void mark_seen(const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z, const Rays &r) {
+    uint16_t *__restrict__ S = reinterpret_cast<uint16_t *>(envk);
+    const uint32_t zbit = 1u << z;
+    const int ntx16 = R.ntx * 16;
+    const int nx = r.x1 - r.x0 + 1, total = nx + (r.y1 - r.y0 + 1);
+    const int ypart = (y >> 2) * ntx16 + (y & 3), xpart = ((x >> 2) << 4) + ((x & 3) << 2);
+    constexpr int RC = G >= 16 ? 2 : 4;                 // cells per lane per chunk: loads of a chunk overlap
+    for (int base = 0; base < total; base += G * RC) {
+        int idx[RC];
+        uint32_t old[RC], msk[RC];
+#pragma unroll
+        for (int q = 0; q < RC; q++) {
+            const int i = base + q * G + lane;
+            int id = -1;
+            msk[q] = zbit;
+            if (i < nx) {
+                const int cx = r.x0 + i;
+                id = ((cx >> 2) << 4) + ((cx & 3) << 2) + ypart;
+                if (cx == x) msk[q] = r.zmask;
+            } else if (i < total) {
+                const int cy = r.y0 + (i - nx);
+                if (cy != y) id = (cy >> 2) * ntx16 + (cy & 3) + xpart;       // centre column belongs to the x run
+            }
+            idx[q] = id;
+            old[q] = id >= 0 ? (uint32_t)S[id] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < RC; q++) {
+            const uint32_t n = old[q] | msk[q];
+            if (idx[q] >= 0 && n != old[q]) S[idx[q]] = (uint16_t)n;
+        }
+    }
+}
+
+// get_obs (CubicEnv.py:254-312) in one piece, for callers that have nothing to overlap with the window loads (reset).
 template <int G>
 NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z,
                       const Rays &r, int centre_count, bool write_seen, const ObsScalars &sc, const float *lut,
                       float *__restrict__ obs_row) {
-    uint16_t *__restrict__ S = reinterpret_cast<uint16_t *>(envk);
-    const uint8_t *__restrict__ C = envk + P.c_off;
-    const uint32_t zbit = 1u << z;
-
     if (obs_row != nullptr) {
-        // Step 2 (:270-275): the 4x4x4 window; one (x,y) column = 4 cells = one float4 of the observation.
-        // Lane -> columns: column j = 4*dxi + dyi with dyi = (lane & 3) + b*G (b < NY) and dxi = (lane >> 2) + a*XS (a < NX),
-        // so the x-dependent and y-dependent halves of every index (they are separable, see s_index / c_index) are
-        // computed once per a / per b instead of once per column.
-        constexpr int NY = G >= 4 ? 1 : 4 / G;               // distinct dy per lane
-        constexpr int NX = G >= 16 ? 1 : (16 / G) / NY;      // distinct dx per lane
-        constexpr int XS = G >= 4 ? G / 4 : 1;               // stride of dxi between a-iterations
-        constexpr int AB = (4 / NY) < NX ? (4 / NY) : NX;    // a-iterations per batch (about 4 columns in flight)
-        const int nbz32 = R.nbz * 32, ntx16 = R.ntx * 16, cys = R.ntx * nbz32;
-        const int zb0 = (z - 2) >> 1;                        // first z-brick of the window (may be -1)
-        const int zsh = ((z - 2) - 2 * zb0) * 8;             // bit offset of cell z-2 inside the 3-brick column word (0 or 8)
-        const uint32_t zvalid = ((((1u << R.H) - 1u) << 2) >> z) & 15u;    // window cells inside [0, H)
-        const bool b0 = zb0 >= 0, b1 = zb0 + 1 < R.nbz, b2 = zsh != 0 && zb0 + 2 < R.nbz;
-        const int zoff = zb0 * 32;
-        const float unknown = lut[1];
-        // y halves
-        int ys[NY], yc[NY], cyv[NY];
-        bool yin[NY], yray[NY];
 #pragma unroll
-        for (int b = 0; b < NY; b++) {
-            const int cy = y + (lane & 3) + b * G - 2;
-            cyv[b] = cy;
-            yin[b] = cy >= 0 && cy < R.D;
-            yray[b] = cy >= r.y0 && cy <= r.y1;
-            ys[b] = (cy >> 2) * ntx16 + (cy & 3);
-            yc[b] = (cy >> 2) * cys + ((cy & 3) << 1) + zoff;
+        for (int a0 = 0; a0 < WinMap<G>::NX; a0 += WinMap<G>::AB) {
+            WinBatch<G> wb;
+            window_load<G>(P, R, envk, lane, x, y, z, a0, wb);
+            window_store<G>(R, lane, x, y, z, a0, wb, r, centre_count, lut, obs_row);
         }
-#pragma unroll
-        for (int a0 = 0; a0 < NX; a0 += AB) {
-            uint32_t sw[AB][NY], ow[AB][NY];
-            unsigned long long cw[AB][NY];
-            bool inb[AB][NY];
-#pragma unroll
-            for (int a = 0; a < AB; a++) {
-                const int dxi = (lane >> 2) + (a0 + a) * XS;
-                const int cx = x + dxi - 2;
-                const bool xin = dxi < 4 && cx >= 0 && cx < R.W;
-                const int xs = ((cx >> 2) << 4) + ((cx & 3) << 2);
-                const int xc = (cx >> 2) * nbz32 + ((cx & 3) << 3);
-                const int xo = cx * R.D;
-#pragma unroll
-                for (int b = 0; b < NY; b++) {
-                    inb[a][b] = xin && yin[b];
-                    sw[a][b] = 0; ow[a][b] = 0; cw[a][b] = 0;
-                    if (inb[a][b]) {
-                        sw[a][b] = S[xs + ys[b]];
-                        ow[a][b] = ldg(P.occz + R.occz_off + (uint32_t)(xo + cyv[b]));
-                        const uint16_t *cp = reinterpret_cast<const uint16_t *>(C + (xc + yc[b]));   // brick zb0 of the column
-                        unsigned long long w = 0;
-                        if (b0) w = cp[0];                                   // bricks are 32 B = 16 u16 apart
-                        if (b1) w |= (unsigned long long)cp[16] << 16;
-                        if (b2) w |= (unsigned long long)cp[32] << 32;
-                        cw[a][b] = w;
-                    }
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < AB; a++) {
-                const int dxi = (lane >> 2) + (a0 + a) * XS;
-                if (dxi >= 4) continue;
-                const int cx = x + dxi - 2;
-                const bool xray = cx >= r.x0 && cx <= r.x1;
-#pragma unroll
-                for (int b = 0; b < NY; b++) {
-                    const int cy = cyv[b];
-                    float4 v = make_float4(unknown, unknown, unknown, unknown);
-                    if (inb[a][b]) {
-                        uint32_t sbits = sw[a][b];
-                        const bool centre_col = (cx == x && cy == y);
-                        if (cy == y && xray) sbits |= centre_col ? r.zmask : zbit;
-                        if (cx == x && yray[b]) sbits |= zbit;
-                        uint32_t c4 = (uint32_t)(cw[a][b] >> zsh);          // byte k = counter of cell z-2+k
-                        if (centre_col) c4 = (c4 & 0xff00ffffu) | ((uint32_t)centre_count << 16);
-                        c4 = vminu4_20(c4) + 0x02020202u;                    // clip at 20 (:273-274), +2 = LUT index of a free cell
-                        const uint32_t s4 = ((sbits << 2) >> z) & zvalid;    // seen, in range
-                        const uint32_t w4 = ((ow[a][b] << 2) >> z) & s4;     // ... and a wall
-                        const uint32_t seen = expand4(s4), wall = expand4(w4);
-                        const uint32_t idx = (c4 & seen & ~wall) | (0x01010101u & ~seen);   // unknown -> 1, known wall -> 0
-                        v.x = lut[idx & 0xffu]; v.y = lut[(idx >> 8) & 0xffu];
-                        v.z = lut[(idx >> 16) & 0xffu]; v.w = lut[idx >> 24];
-                    }
-                    store_stream(reinterpret_cast<float4 *>(obs_row) + (dxi * 4 + (cy - y + 2)), v);
-                }
-            }
-        }
-        // Steps 3-6: the 9 scalars + zero padding = 4 more float4 (:279-307)
-        for (int j = 16 + lane; j < 20; j += G) {
-            float4 v;
-            if (j == 16) {
-                v.x = sc.facing == 0 ? 1.f : 0.f; v.y = sc.facing == 1 ? 1.f : 0.f;
-                v.z = sc.facing == 2 ? 1.f : 0.f; v.w = sc.facing == 3 ? 1.f : 0.f;
-            } else if (j == 17) {
-                // float(k)/5, count/L and visited/total are f64 quotients rounded to f32 in the reference (:284-291); for
-                // integers below 2^24 that equals the correctly rounded f32 quotient (53 >= 2*24+2, Figueroa 1995).
-                v.x = fdiv_rn((float)sc.last_action, 5.0f);
-                v.y = (float)sc.was_near_wall;
-                v.z = (float)sc.last_bump;
-                v.w = fdiv_rn((float)sc.down, (float)P.L);
-            } else if (j == 18) {
-                v.x = fdiv_rn((float)sc.visited, (float)sc.total_free);
-                v.y = v.z = v.w = 0.f;
-            } else {
-                v.x = v.y = v.z = v.w = 0.f;
-            }
-            store_stream(reinterpret_cast<float4 *>(obs_row) + j, v);
-        }
+        write_scalars<G>(P, lane, sc, obs_row);
     }
-
-    // Step 1 (:264-266): mark every cell the six rays examined as seen.  (Done after the gather in program order — the
-    // gather re-derives these bits from the ray extents — so that its stores do not fence the window loads.)
-    if (write_seen) {
-        const int nx = r.x1 - r.x0 + 1, total = nx + (r.y1 - r.y0 + 1);
-        constexpr int RC = G >= 16 ? 2 : 4;                 // cells per lane per chunk: loads of a chunk overlap
-        for (int base = 0; base < total; base += G * RC) {
-            uint32_t idx[RC], old[RC], msk[RC];
-#pragma unroll
-            for (int q = 0; q < RC; q++) {
-                const int i = base + q * G + lane;
-                int cx = x, cy = y;
-                bool valid = i < total;
-                if (i < nx) cx = r.x0 + i;
-                else { cy = r.y0 + (i - nx); valid = valid && cy != y; }      // centre column belongs to the x run
-                msk[q] = (cx == x && cy == y) ? r.zmask : zbit;
-                idx[q] = valid ? s_index(R, cx, cy) : 0xffffffffu;
-                old[q] = valid ? (uint32_t)S[idx[q]] : 0u;
-            }
-#pragma unroll
-            for (int q = 0; q < RC; q++) {
-                const uint32_t n = old[q] | msk[q];
-                if (idx[q] != 0xffffffffu && n != old[q]) S[idx[q]] = (uint16_t)n;
-            }
-        }
-    }
+    if (write_seen) mark_seen<G>(R, envk, lane, x, y, z, r);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -432,7 +468,8 @@ NAV3D_HD void reset_env(const EngineParams &P, int env, int lane, int lane_in_wa
     if (lane == 0) {
         EnvState st;
         st.x = (uint8_t)x; st.y = (uint8_t)y; st.z = (uint8_t)z; st.facing = 0;
-        st.last_action = 0; st.flags = (uint8_t)(r.near_wall ? kNearWall : 0u); st.down = (uint8_t)r.down; st.pad0 = 0;
+        st.last_action = 0; st.flags = (uint8_t)(r.near_wall ? kNearWall : 0u); st.down = (uint8_t)r.down;
+        st.pad0 = (uint8_t)r.blocked6;
         st.step_count = 0; st.visited_count = 1; st.bump_count = 0; st.ret_centi = 0;
         st.episode = episode_after; st.room = (uint16_t)room_idx; st.pad1 = 0;
         P.states[env] = st;
@@ -470,51 +507,61 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
     const uint32_t step_count = st.step_count + 1u;                              // :115
     const bool truncated = step_count >= R.n_free;                               // :116, max_steps = total_free (:459)
 
-    // do_action (:134-166)
+    // do_action (:134-166).  Whether the move bumps was worked out by the previous step's rays (record byte `pad0`), so
+    // the new position — and with it every address this step touches — is known as soon as the record arrives.
     int x = st.x, y = st.y, z = st.z, facing = st.facing;
-    int tx = x, ty = y, tz = z;
+    uint32_t dir;                                                                // index into blocked6
     if (a < 4) {
         facing = (facing + a) & 3;                                               // table :135-140 == rotate by a; :148-151
-        tx += (facing == 1) - (facing == 3);
-        ty += (facing == 0) - (facing == 2);
-    } else tz += (a == 4) ? 1 : -1;
-    bool moved = false;
-    if (tx >= 0 && tx < R.W && ty >= 0 && ty < R.D && tz >= 0 && tz < R.H) {     // _mark_visited :328-332
-        const uint32_t ow = ldg(P.occz + R.occz_off + (uint32_t)(tx * R.D + ty));
-        moved = !((ow >> tz) & 1u);
+        dir = (0x1302u >> (facing * 4)) & 3u;                                    // N -> +y (2), E -> +x (0), S -> -y (3), W -> -x (1)
+    } else dir = (uint32_t)a;                                                    // 4 -> +z, 5 -> -z
+    const bool moved = !((st.pad0 >> dir) & 1u);                                 // _mark_visited :328-332
+    if (moved) {
+        x += (dir == 0) - (dir == 1);
+        y += (dir == 2) - (dir == 3);
+        z += (dir == 4) - (dir == 5);
     }
-    if (moved) { x = tx; y = ty; z = tz; }
+    const bool bumped = !moved;
+
+    // Issue every load of the step now: first window batch, the counter of the final cell, the three occupancy words.
+    WinBatch<G> wb;
+    window_load<G>(P, R, envk, lane, x, y, z, 0, wb);
     const uint32_t cidx = c_index(R, x, y, z);
     const int c_old = C[cidx];
+    const Rays r = cast_rays(P, R, x, y, z);
+
     // entering: 0 -> 1 (+visited, explored) or v -> v+1 (:335-341); then the unconditional += 1 at the final
     // position (:165-166).  A bump only gets the latter.
     const bool explored = moved && c_old == 0;
     const int c_new = imin(255, c_old + (moved ? 2 : 1));
     if (lane == 0) C[cidx] = (uint8_t)c_new;
     const uint32_t visited = st.visited_count + (explored ? 1u : 0u);
-    const bool bumped = !moved;
 
     // termination test of compute_reward (:212-214): visited/total >= 0.84 in f64.  For total <= 65536 this is
     // exactly 25*visited >= 21*total (tests/test_host_logic.py::test_finish_threshold_integer_form).
-    const bool done = (25ull * visited >= 21ull * R.n_free) ;
+    const bool done = 25u * visited >= 21u * R.n_free;
     const bool will_reset = P.auto_reset && (done || truncated);
 
     // get_obs (:122)
-    Rays r;
     float *orow = io.obs + row * kObsDim;
     if (will_reset) orow = io.terminal_obs ? io.terminal_obs + row * kObsDim : nullptr;
-    const bool need_obs = !will_reset || orow != nullptr;
-    if (need_obs) {
-        r = cast_rays(P, R, x, y, z);
+    if (orow != nullptr) {
         ObsScalars sc;
         sc.facing = facing; sc.last_action = st.last_action; sc.was_near_wall = (flags & kWasNearWall) != 0;
         sc.last_bump = (flags & kLastBump) != 0; sc.down = r.down; sc.visited = visited; sc.total_free = R.n_free;
-        // The cells a ray pass marks depend only on the position (L and the room are fixed), and marks are never erased
-        // within an episode: every earlier stay at this cell (c_old >= 1, which includes every bump) already marked
-        // them.  Only a FIRST visit has anything to write, so revisits skip the ray marking and its scattered traffic.
-        observe<G>(P, R, envk, lane, x, y, z, r, c_new, !will_reset && explored, sc, lut, orow);
-        if (r.near_wall) flags |= kNearWall;
-    } else { r.down = 0; }
+        window_store<G>(R, lane, x, y, z, 0, wb, r, c_new, lut, orow);
+#pragma unroll
+        for (int a0 = WinMap<G>::AB; a0 < WinMap<G>::NX; a0 += WinMap<G>::AB) {
+            window_load<G>(P, R, envk, lane, x, y, z, a0, wb);
+            window_store<G>(R, lane, x, y, z, a0, wb, r, c_new, lut, orow);
+        }
+        write_scalars<G>(P, lane, sc, orow);
+    }
+    // The cells a ray pass marks depend only on the position (L and the room are fixed), and marks are never erased
+    // within an episode: every earlier stay at this cell (c_old >= 1, which includes every bump) already marked
+    // them.  Only a FIRST visit has anything to write, so revisits skip the ray marking and its scattered traffic.
+    if (explored && !will_reset) mark_seen<G>(R, envk, lane, x, y, z, r);
+    if (r.near_wall) flags |= kNearWall;
 
     if (lane == 0) {
         // compute_reward (:169-224), same operations in the same order, f64
@@ -551,7 +598,7 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
         if (!will_reset) {
             EnvState ns;
             ns.x = (uint8_t)x; ns.y = (uint8_t)y; ns.z = (uint8_t)z; ns.facing = (uint8_t)facing;
-            ns.last_action = (uint8_t)a; ns.flags = (uint8_t)flags; ns.down = (uint8_t)r.down; ns.pad0 = 0;
+            ns.last_action = (uint8_t)a; ns.flags = (uint8_t)flags; ns.down = (uint8_t)r.down; ns.pad0 = (uint8_t)r.blocked6;
             ns.step_count = step_count; ns.visited_count = visited; ns.bump_count = bump_count;
             ns.ret_centi = ret_centi; ns.episode = st.episode; ns.room = st.room; ns.pad1 = 0;
             P.states[env] = ns;
