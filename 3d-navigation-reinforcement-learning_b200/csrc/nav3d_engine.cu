@@ -405,6 +405,8 @@ int check_ready(const nav3d_engine *e) {
 
 }  // namespace
 
+namespace nav3d { int fail_with(int code, const std::string &msg) { return fail(code, msg); } }   // for nav3d_train.cu
+
 extern "C" {
 
 const char *nav3d_last_error(void) { return g_err.c_str(); }

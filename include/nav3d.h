@@ -167,6 +167,26 @@ size_t nav3d_snapshot_bytes(const nav3d_engine *e);
 int nav3d_snapshot(nav3d_engine *e, void *host_buf, size_t bytes);
 int nav3d_restore(nav3d_engine *e, const void *host_buf, size_t bytes);
 
+/* ---- rollout-loop kernels of the LSTM-PPO trainer.  Engine-free: they run on the CUDA device that is
+ * current on the calling thread; all buffers are DEVICE pointers; asynchronous on `stream`.  They replace, in the
+ * reference's third-party stack (sb3-contrib RecurrentPPO driven by train/Grid_Train.py:198-228), the per-step
+ * `distribution.get_actions()/log_prob()` and `RecurrentRolloutBuffer.compute_returns_and_advantage`. ---- */
+
+/* Categorical sampling from policy logits f32[n][n_actions] (row-major).  u = word 0 of Philox4x32-10 with
+ * counter = (env_id0 + i, step, 0, 0x504f4c49) and the key of `seed`; action = first k with cumsum(softmax)[k] > u.
+ * greedy != 0: argmax instead (SB3's deterministic=True, train/evaluate_grid.py:186-191).
+ *   actions : int64[n] (directly usable by nav3d_step)   log_prob : f32[n] or NULL   entropy : f32[n] or NULL */
+int nav3d_sample_actions(const float *logits, int32_t n, int32_t n_actions, uint64_t seed, uint32_t env_id0,
+                         uint32_t step, int32_t greedy, int64_t *actions, float *log_prob, float *entropy, void *stream);
+
+/* GAE(lambda) over a time-major rollout: rewards, values f32[T][n]; episode_starts u8[T][n] (1 = step t is the first of
+ * an episode); last_values f32[n] = V(s_T); last_dones u8[n] = the episode ended at step T-1.
+ *   A_t = delta_t + gamma*lambda*(1-start_{t+1})*A_{t+1},  delta_t = r_t + gamma*V_{t+1}*(1-start_{t+1}) - V_t
+ *   advantages, returns (= A + V) : f32[T][n] */
+int nav3d_gae(const float *rewards, const float *values, const uint8_t *episode_starts, const float *last_values,
+              const uint8_t *last_dones, float gamma, float gae_lambda, int32_t T, int32_t n, float *advantages,
+              float *returns, void *stream);
+
 /* Number of CUDA kernels this library has launched since the engine was created (bench.py's gpu_launches). */
 uint64_t nav3d_launch_count(const nav3d_engine *e);
 /* Bytes of device memory the engine holds. */

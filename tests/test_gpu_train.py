@@ -1,0 +1,117 @@
+"""-m gpu: the rollout-loop kernels (csrc/nav3d_train.cu, through the C ABI) against their plain-PyTorch fp32
+restatements, and the LSTM-PPO trainer end to end on the GPU-resident env."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOMS
+from train_refs import gae_reference
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from nav3d.train_ops import DeviceOps
+    return DeviceOps(seed=1234, env_id0=0)
+
+
+@pytest.mark.parametrize("T,N", [(1, 1), (7, 33), (64, 5000), (2048, 8)])
+def test_gae_kernel_matches_torch_reference(ops, T, N):
+    g = torch.Generator(device="cuda").manual_seed(T * 1000 + N)
+    dev = "cuda"
+    r = torch.randn((T, N), generator=g, device=dev)
+    v = torch.randn((T, N), generator=g, device=dev)
+    s = (torch.rand((T, N), generator=g, device=dev) < 0.05).to(torch.uint8)
+    lv = torch.randn(N, generator=g, device=dev)
+    ld = (torch.rand(N, generator=g, device=dev) < 0.3).to(torch.uint8)
+    adv, ret = torch.empty_like(r), torch.empty_like(r)
+    ops.gae(r, v, s, lv, ld, 0.99, 0.95, adv, ret)
+    want_a, want_r = gae_reference(r.cpu(), v.cpu(), s.cpu(), lv.cpu(), ld.cpu(), 0.99, 0.95)
+    # fp32 on both sides; the kernel fuses multiply-adds, so allow a few ulp of the running sum (tolerance 1e-5 relative
+    # to the largest advantage in the column)
+    scale = want_a.abs().max().item() + 1.0
+    assert (adv.cpu() - want_a).abs().max().item() <= 1e-5 * scale
+    assert (ret.cpu() - want_r).abs().max().item() <= 1e-5 * scale
+
+
+def test_sample_actions_logprob_entropy_greedy(ops):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    logits = 3.0 * torch.randn((4099, 6), generator=g, device="cuda")
+    ent = torch.empty(4099, device="cuda")
+    a, lp = ops.sample_actions(logits, step=3, entropy=ent)
+    ref = torch.log_softmax(logits, dim=-1)
+    assert a.dtype == torch.int64 and int(a.min()) >= 0 and int(a.max()) <= 5
+    assert torch.allclose(lp, ref.gather(-1, a.unsqueeze(-1)).squeeze(-1), atol=2e-6, rtol=1e-5)
+    assert torch.allclose(ent, -(ref.exp() * ref).sum(-1), atol=2e-6, rtol=1e-5)
+    ga, glp = ops.sample_actions(logits, step=3, greedy=True)
+    assert torch.equal(ga, logits.argmax(-1))
+    assert torch.allclose(glp, ref.max(-1).values, atol=2e-6, rtol=1e-5)
+    # deterministic in (seed, env id, step); a different step gives a different draw
+    a2, _ = ops.sample_actions(logits, step=3)
+    a3, _ = ops.sample_actions(logits, step=4)
+    assert torch.equal(a, a2) and not torch.equal(a, a3)
+
+
+def test_sample_actions_distribution_and_shard_independence():
+    from nav3d.train_ops import DeviceOps
+    N = 600_000
+    probs = torch.tensor([0.05, 0.4, 0.1, 0.25, 0.15, 0.05])
+    logits = probs.log().repeat(N, 1).cuda().contiguous()
+    full = DeviceOps(seed=77, env_id0=0)
+    a, _ = full.sample_actions(logits, step=11)
+    counts = torch.bincount(a, minlength=6).cpu().double()
+    expected = probs.double() * N
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    assert chi2 < 25.7, (chi2, counts)                     # 5 dof, p = 1e-4
+    # two shards keyed by global env id reproduce the single-shard draw
+    half = N // 2
+    lo, _ = DeviceOps(seed=77, env_id0=0).sample_actions(logits[:half], step=11)
+    hi, _ = DeviceOps(seed=77, env_id0=half).sample_actions(logits[half:], step=11)
+    assert torch.equal(torch.cat([lo, hi]), a)
+    # successive steps are independent: lag-1 agreement is what independence predicts
+    b, _ = full.sample_actions(logits, step=12)
+    agree = float((a == b).double().mean())
+    assert abs(agree - float((probs ** 2).sum())) < 0.005
+
+
+def test_train_ops_reject_cpu_tensors(ops):
+    with pytest.raises(RuntimeError):
+        ops.sample_actions(torch.zeros((4, 6)), step=0)
+
+
+def test_ppo_learns_on_gpu_env(tmp_path):
+    """A short run on the 12x12x12 room: bookkeeping, finite statistics, checkpoint round trip, and the mean reward per
+    step of the rollouts rises as the policy stops bumping into walls."""
+    from nav3d import BatchedCubicEnv
+    from nav3d.evaluation import EvalCallback, evaluate_policy
+    from nav3d.ppo import RecurrentPPO
+    from nav3d.rooms import load_room_file
+    room = load_room_file(ROOMS / "P1_training" / "Empty_room_3mx3mx3m_0.25m_cellsize.txt")
+    env = BatchedCubicEnv(rooms=[room], num_envs=512, local_map_length=10, seed=3)
+    eval_env = BatchedCubicEnv(rooms=[room], num_envs=8, local_map_length=10, seed=4)
+    model = RecurrentPPO(env, policy_kwargs=dict(net_arch=dict(pi=[256, 256, 128], vf=[256, 256, 128]), lstm_hidden_size=256,
+                                                 n_lstm_layers=1),
+                         learning_rate=3e-4, n_steps=64, batch_size=64 * 128, n_epochs=4, gamma=0.99, gae_lambda=0.95,
+                         ent_coef=0.01, vf_coef=0.5, clip_range=0.2, seed=0)
+    cb = EvalCallback(eval_env, best_model_save_path=tmp_path, log_path=tmp_path, eval_freq=64 * 10, n_eval_episodes=8, verbose=0)
+    launches0 = env.engine.launch_count
+    model.learn(total_timesteps=30 * 64 * 512, callback=cb)
+    assert model.num_timesteps == 30 * 64 * 512 and len(model.logger) == 30
+    assert env.engine.launch_count - launches0 >= 30 * 64          # every rollout step is a nav3d_step launch
+    for rec in model.logger:
+        assert all(math.isfinite(rec[k]) for k in ("loss", "policy_loss", "value_loss", "entropy_loss", "approx_kl"))
+    first = np.mean([r["rollout_reward_mean"] for r in model.logger[:3]])
+    last = np.mean([r["rollout_reward_mean"] for r in model.logger[-3:]])
+    assert last > first + 0.05, (first, last)
+    assert len(cb.evaluations_timesteps) == 3 and (tmp_path / "best_model.zip").exists()
+    path = model.save(tmp_path / "ckpt")
+    again = RecurrentPPO.load(path, env=env)
+    obs = torch.rand((16, 80), device=env.device)
+    a1, _ = model.predict(obs, deterministic=True)
+    a2, _ = again.predict(obs, deterministic=True)
+    assert torch.equal(a1, a2)
+    st = evaluate_policy(again, eval_env, n_eval_episodes=8, return_episode_stats=True)
+    assert len(st["r"]) == 8 and (st["total_free"] == 1000).all()
