@@ -83,29 +83,32 @@ def test_train_ops_reject_cpu_tensors(ops):
 
 
 def test_ppo_learns_on_gpu_env(tmp_path):
-    """A short run on the 12x12x12 room: bookkeeping, finite statistics, checkpoint round trip, and the mean reward per
-    step of the rollouts rises as the policy stops bumping into walls."""
+    """A short run on an 8x8x6 hollow box (144 free cells, so 144-step episodes): bookkeeping, finite statistics, the
+    evaluation callback, a checkpoint round trip — and the policy learns (episode return rises from about -1 for the
+    untrained policy to above +20 within 0.8 M steps; measured curve in DESIGN.md)."""
     from nav3d import BatchedCubicEnv
     from nav3d.evaluation import EvalCallback, evaluate_policy
     from nav3d.ppo import RecurrentPPO
-    from nav3d.rooms import load_room_file
-    room = load_room_file(ROOMS / "P1_training" / "Empty_room_3mx3mx3m_0.25m_cellsize.txt")
-    env = BatchedCubicEnv(rooms=[room], num_envs=512, local_map_length=10, seed=3)
-    eval_env = BatchedCubicEnv(rooms=[room], num_envs=8, local_map_length=10, seed=4)
+    from nav3d.rooms import rooms_from_grids
+    g = np.zeros((8, 8, 6), dtype=np.int8)
+    g[0], g[-1], g[:, 0], g[:, -1], g[:, :, 0], g[:, :, -1] = -2, -2, -2, -2, -2, -2
+    rooms = rooms_from_grids([g])
+    env = BatchedCubicEnv(rooms=rooms, num_envs=256, local_map_length=10, seed=3)
+    eval_env = BatchedCubicEnv(rooms=rooms, num_envs=8, local_map_length=10, seed=4)
     model = RecurrentPPO(env, policy_kwargs=dict(net_arch=dict(pi=[256, 256, 128], vf=[256, 256, 128]), lstm_hidden_size=256,
                                                  n_lstm_layers=1),
-                         learning_rate=3e-4, n_steps=64, batch_size=64 * 128, n_epochs=4, gamma=0.99, gae_lambda=0.95,
+                         learning_rate=3e-4, n_steps=64, batch_size=64 * 64, n_epochs=4, gamma=0.99, gae_lambda=0.95,
                          ent_coef=0.01, vf_coef=0.5, clip_range=0.2, seed=0)
-    cb = EvalCallback(eval_env, best_model_save_path=tmp_path, log_path=tmp_path, eval_freq=64 * 10, n_eval_episodes=8, verbose=0)
+    iters = 48
+    cb = EvalCallback(eval_env, best_model_save_path=tmp_path, log_path=tmp_path, eval_freq=64 * 16, n_eval_episodes=8, verbose=0)
     launches0 = env.engine.launch_count
-    model.learn(total_timesteps=30 * 64 * 512, callback=cb)
-    assert model.num_timesteps == 30 * 64 * 512 and len(model.logger) == 30
-    assert env.engine.launch_count - launches0 >= 30 * 64          # every rollout step is a nav3d_step launch
+    model.learn(total_timesteps=iters * 64 * 256, callback=cb)
+    assert model.num_timesteps == iters * 64 * 256 and len(model.logger) == iters
+    assert env.engine.launch_count - launches0 >= iters * 64       # every rollout step is a nav3d_step launch
     for rec in model.logger:
         assert all(math.isfinite(rec[k]) for k in ("loss", "policy_loss", "value_loss", "entropy_loss", "approx_kl"))
-    first = np.mean([r["rollout_reward_mean"] for r in model.logger[:3]])
-    last = np.mean([r["rollout_reward_mean"] for r in model.logger[-3:]])
-    assert last > first + 0.05, (first, last)
+    curve = [r["ep_rew_mean"] for r in model.logger if math.isfinite(r["ep_rew_mean"])]
+    assert curve[-1] > curve[0] + 10.0, (curve[0], curve[-1])
     assert len(cb.evaluations_timesteps) == 3 and (tmp_path / "best_model.zip").exists()
     path = model.save(tmp_path / "ckpt")
     again = RecurrentPPO.load(path, env=env)
@@ -114,4 +117,4 @@ def test_ppo_learns_on_gpu_env(tmp_path):
     a2, _ = again.predict(obs, deterministic=True)
     assert torch.equal(a1, a2)
     st = evaluate_policy(again, eval_env, n_eval_episodes=8, return_episode_stats=True)
-    assert len(st["r"]) == 8 and (st["total_free"] == 1000).all()
+    assert len(st["r"]) == 8 and (st["total_free"] == 144).all()
