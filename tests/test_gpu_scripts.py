@@ -18,7 +18,7 @@ def test_grid_train_then_train_further_then_evaluate(tmp_path, monkeypatch, caps
     from train import Grid_Train, Train_Further, evaluate_grid
     save = tmp_path / "exp3_architectures"
     Grid_Train.main(["--native", "--num-envs", "64", "--steps", str(10 * 128 * 64), "--save-dir", str(save),
-                     "--eval-freq", str(5 * 128 * 64)])
+                     "--eval-freq", str(128 * 64)])   # one evaluation per segment (the callback is re-created per segment)
     stem = "rppo_hp1_arch_pi[256, 256, 128]_vf[256, 256, 128]_lstm_h256l1_shared"
     names = sorted(p.name for p in save.glob("*.zip"))
     assert names == sorted(f"{stem}_s{(i + 1) * 128 * 64}_view10.zip" for i in range(10))
