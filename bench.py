@@ -252,6 +252,46 @@ def time_e2e(eng, n, steps, torch, dist, world):
     return sec, n * 8, n * (80 * 4 + 4 + 1 + 1), checksum
 
 
+def time_training(torch, dist, world, rank, local_rank, n_envs=4096, n_steps=128, iters=3):
+    """BASELINE configs[4] (not roofline-graded): LSTM-PPO with the Grid_Train hyper-parameters on P1_training, env and
+    rollout resident on the GPU, one rank per GPU with an NCCL gradient all-reduce per minibatch.  Weak scaling: every rank
+    owns n_envs envs.  Returns env-steps/s over rollout + update, all ranks."""
+    from nav3d import BatchedCubicEnv
+    from nav3d.ppo import RecurrentPPO
+    env = BatchedCubicEnv(ROOT / "rooms" / "P1_training", num_envs=n_envs, local_map_length=10, seed=42, sort_rooms=True,
+                          device=local_rank, env_id0=rank * n_envs)
+    model = RecurrentPPO(env, policy_kwargs=dict(net_arch=dict(pi=[256, 256, 128], vf=[256, 256, 128]), lstm_hidden_size=256,
+                                                 n_lstm_layers=1),
+                         learning_rate=3e-4, n_steps=n_steps, batch_size=512 * n_steps, n_epochs=10, gamma=0.99,
+                         gae_lambda=0.95, ent_coef=0.01, vf_coef=0.5, clip_range=0.2, seed=42)
+    model.collect_rollouts(); model.train()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_roll = t_train = 0.0
+    for _ in range(iters):
+        t0 = time.perf_counter(); model.collect_rollouts(); torch.cuda.synchronize(); t1 = time.perf_counter()
+        stats = model.train(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        t_roll += t1 - t0; t_train += t2 - t1
+    sec = t_roll + t_train
+    if world > 1:
+        dist.barrier()
+        tmax = torch.tensor([sec], device=env.device, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sec = float(tmax.item())
+    steps = iters * n_steps * n_envs * world
+    out = {"workload": "BASELINE configs[4]: LSTM-PPO (MlpLstmPolicy 80->LSTM256 x2->256-256-128, Grid_Train hyper-parameters, "
+                       f"{n_envs} envs x {n_steps} steps per GPU per rollout, 512-env minibatches, 10 epochs) on P1_training, "
+                       "GPU-resident env, NCCL gradient all-reduce per minibatch",
+           "value": steps / sec, "unit": "env-steps/s (rollout + PPO update)", "iters": iters, "n_gpus": world,
+           "rollout_share": t_roll / (t_roll + t_train), "rollout_steps_per_s_rank0": iters * n_steps * n_envs / t_roll,
+           "minibatches_per_update": stats["minibatches"], "scaling": "weak"}
+    env.close()
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,12 +362,17 @@ def main():
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": f"step_kernel<{eng.lanes_per_env}>",
+                "traffic": traffic, "kernel": f"step_call_kernel<{eng.lanes_per_env}>",
                 "algorithmic_bytes_per_env_step": balg, "env_steps_per_launch": n_local,
                 "launch_ms": launch_ms, "peak_source": peak_src}
 
     extra = {}
     cpu_baseline = None
+    if not args.no_extras:
+        try:
+            extra["c5_train"] = time_training(torch, dist, world, rank, local_rank)
+        except Exception as ex:  # noqa: BLE001
+            extra["c5_train"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_extras:
         # secondary workloads, same timing method (short)
         del eng
