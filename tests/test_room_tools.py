@@ -1,0 +1,93 @@
+"""Room tooling: the writer inverts the parser on all 60 shipped rooms, the validator finds the quirks
+SURVEY §8c lists, generated rooms are valid, deterministic and load into the oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import ROOMS
+from nav3d.room_tools import (generate_room, main, normalise_room_text, room_to_text, validate_room_file,
+                              validate_room_text)
+from nav3d.rooms import parse_room_text
+
+ALL_ROOMS = sorted(ROOMS.glob("*/*.txt"))
+
+
+def test_writer_inverts_parser_on_every_shipped_room():
+    assert len(ALL_ROOMS) == 60
+    for f in ALL_ROOMS:
+        text = f.read_text()
+        room = parse_room_text(text)
+        again = parse_room_text(room_to_text(room.grid, room.start, room.goal))
+        assert np.array_equal(room.grid, again.grid) and room.start == again.start and room.goal == again.goal, f.name
+        assert np.array_equal(parse_room_text(normalise_room_text(text)).grid, room.grid), f.name
+        simple = parse_room_text(text, simple=True)
+        back = parse_room_text(room_to_text(simple.grid, cubic=False), simple=True)
+        assert np.array_equal(simple.grid, back.grid), f.name
+
+
+def test_validator_finds_the_known_quirks(rooms_json):
+    reports = {f"{f.parent.name}/{f.name}": validate_room_file(f) for f in ALL_ROOMS}
+    assert not any(r.errors for r in reports.values())
+    k2 = reports["P3_training/kitchen2.txt"]
+    assert k2.findings["negative_layer_index"] == {-2: 10} and k2.findings.get("literal_minus_two") is True
+    assert "open_shell_cells" in k2.findings
+    open_shell = sorted(n for n, r in reports.items() if "open_shell_cells" in r.findings)
+    # rooms whose boundary shell is not all wall
+    assert all(("maze_7x7" in n or "maze_8x8" in n or "maze_dead1_11" in n or n.endswith("kitchen2.txt")) for n in open_shell)
+    assert any("maze_7x7" in n for n in open_shell) and "P3_training/kitchen2.txt" in open_shell
+    # against the fixture generated from the unmodified reference (tests/golden/rooms.json)
+    assert set(rooms_json) == set(reports)
+    for n, rep in reports.items():
+        want = rooms_json[n]
+        assert rep.n_free_interior == want["total_free_cells"] and rep.n_wall == want["n_wall_cells"], n
+        assert list(rep.dims) == want["dims"] and ("open_shell_cells" not in rep.findings) == want["shell_closed"], n
+    assert reports["P1_training/Empty_room_3mx3mx3m_0.25m_cellsize.txt"].ok
+
+
+def test_validator_reports_malformed_files():
+    r = validate_room_text("Size=3,3,3\nLayer z=0\n2 2\n")
+    assert r.errors and "ValueError" in r.errors[0]
+    r = validate_room_text("Size=4,4,4\nLayer z=0\n" + "2 2 2 2\n" * 4 + "Layer z=3\n" + "2 2 2 2\n" * 4 +
+                           "Layer z=1\n2 2 2 2\n2 0 7 2\n2 0 0 2\n2 2 2 2\nStart position=0,0,0\n")
+    assert r.findings["missing_layers"] == [2] and r.findings["stray_values"] == [7]
+    assert r.findings["start_in_wall"] == (0, 0, 0) and "open_shell_cells" in r.findings
+    r = validate_room_text("Size=3,3,3\n" + "".join(f"Layer z={z}\n" + "2 2 2\n" * 3 for z in range(3)))
+    assert any("no free interior" in e for e in r.errors)
+    # two sealed chambers: neither reaches 84 %
+    g = generate_room("empty", (9, 5, 5))
+    g[4] = -2
+    r = validate_room_text(room_to_text(g))
+    assert r.findings["largest_connected_free_fraction"] == 0.5
+
+
+@pytest.mark.parametrize("kind,size", [("empty", (20, 20, 12)), ("maze", (21, 21, 9)), ("maze", (48, 32, 12)), ("furnished", (32, 32, 12))])
+def test_generated_rooms_are_valid_and_deterministic(kind, size, oracle):
+    g = generate_room(kind, size, seed=5)
+    assert g.shape == size and np.array_equal(g, generate_room(kind, size, seed=5))
+    if kind != "empty":
+        assert not np.array_equal(g, generate_room(kind, size, seed=6))
+    rep = validate_room_text(room_to_text(g), name=kind)
+    assert not rep.errors and "open_shell_cells" not in rep.findings and rep.n_free_interior > 0
+    if kind in ("empty", "maze"):
+        assert "largest_connected_free_fraction" not in rep.findings        # connected by construction
+    room = oracle.OracleRoom(parse_room_text(room_to_text(g)).grid, -2)
+    assert room.n_free == rep.n_free_interior
+    env = oracle.OracleCubic(10, -2.0) if hasattr(oracle, "OracleCubic") else None
+    if env is not None:
+        env.reset(room, room.free_cell(0))
+        for a in (0, 1, 2, 3, 4, 5):
+            env.step(a)
+
+
+def test_cli_validate_and_generate(tmp_path, capsys):
+    out = tmp_path / "m.txt"
+    assert main(["generate", "--kind", "maze", "--size", "11,11,5", "--seed", "2", "-o", str(out)]) == 0
+    assert out.read_text().startswith("Size=11,11,5\nLayer z=0\n")
+    assert main(["validate", str(out)]) == 0
+    assert main(["validate", str(ROOMS / "P3_training")]) == 0
+    txt = capsys.readouterr().out
+    assert "kitchen2.txt" in txt and "negative_layer_index" in txt
+    norm = tmp_path / "k2.txt"
+    assert main(["normalise", str(ROOMS / "P3_training" / "kitchen2.txt"), "-o", str(norm)]) == 0
+    assert validate_room_file(norm).findings.get("negative_layer_index") is None
