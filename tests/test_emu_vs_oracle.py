@@ -55,6 +55,16 @@ def test_emu_ray_lengths(oracle, L):
     run_lockstep(oracle, rooms, n=24, L=L, steps=400, seed=L, crash=-0.5)
 
 
+def test_emu_engine_limits_and_degenerate_rooms(oracle):
+    from edge_rooms import degenerate_rooms, max_size_rooms, thin_open_rooms
+    assert run_lockstep(oracle, max_size_rooms(), n=12, L=15, steps=600, seed=2, check_state_every=5) >= 0
+    assert run_lockstep(oracle, degenerate_rooms(), n=16, L=10, steps=300, seed=4) > 0
+    assert run_lockstep(oracle, thin_open_rooms(), n=12, L=4, steps=200, seed=6) > 0
+    # counters beyond the u8 range: no auto-reset in the two-cell room, 400 steps (the oracle's int64 grid is compared
+    # after clamping to 255; observations clip at 20 and rewards at 25, so every output stays identical)
+    run_lockstep(oracle, degenerate_rooms()[3:], n=4, L=10, steps=400, seed=8, auto_reset=False)
+
+
 def test_emu_no_autoreset_runs_past_done(oracle):
     rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt")]
     run_lockstep(oracle, rooms, n=8, L=10, steps=400, seed=5, auto_reset=False)

@@ -208,6 +208,48 @@ def test_both_reset_paths_and_occupancy_variants(oracle, monkeypatch, inline, mi
     assert n_done > 1500
 
 
+@pytest.mark.parametrize("lanes", [1, 4, 32])
+def test_engine_limits_and_degenerate_rooms(oracle, lanes):
+    """64x64x16 rooms (bit 63 / bit 15 of the packed words, open boundary faces), single-cell / corridor / slab rooms,
+    wall-less rooms, and visit counters past the u8 range."""
+    from edge_rooms import degenerate_rooms, max_size_rooms, thin_open_rooms
+    lockstep(oracle, max_size_rooms(), n=300, L=15, steps=500, seed=2, lanes=lanes, state_every=25)
+    assert lockstep(oracle, degenerate_rooms(), n=400, L=10, steps=300, seed=4, lanes=lanes) > 0
+    assert lockstep(oracle, thin_open_rooms(), n=300, L=4, steps=200, seed=6, lanes=lanes) > 0
+    lockstep(oracle, degenerate_rooms()[3:], n=64, L=10, steps=400, seed=8, lanes=lanes, auto_reset=False)
+
+
+def test_snapshot_restore_replays_identically(oracle):
+    """nav3d_snapshot / nav3d_restore: the complete mutable state (records + knowledge) round-trips through host memory."""
+    import torch
+    from gpu_harness import GpuEngine
+    rooms = load_room_dir(ROOMS / "P3_training", sort=True)
+    n = 700
+    g = GpuEngine(n, rooms, 10, -2.0, 13, 0, True, 4)
+    g.reset()
+    rng = np.random.default_rng(1)
+    acts = rng.integers(0, 6, size=(260, n))
+    for t in range(130):
+        g.step(acts[t], pull=False)
+    snap = g.eng.snapshot()
+    assert snap.nbytes > n * 32
+    first = []
+    for t in range(130, 260):
+        g.step(acts[t])
+        first.append((g.obs.copy(), g.reward64.copy(), g.term.copy(), g.trunc.copy(), g.eps.copy()))
+    st1, grid1 = g.state().copy(), g.grid(5).copy()
+    g.eng.restore(snap)
+    for t in range(130, 260):
+        g.step(acts[t])
+        o, r, te, tr, ep = first[t - 130]
+        assert np.array_equal(g.obs.view(np.uint32), o.view(np.uint32)) and np.array_equal(g.reward64, r)
+        assert np.array_equal(g.term, te) and np.array_equal(g.trunc, tr)
+    assert np.array_equal(g.state(), st1) and np.array_equal(g.grid(5), grid1)
+    with pytest.raises(Exception):
+        g.eng.restore(snap[:-1])
+    torch.cuda.synchronize()
+
+
 def test_scalar_facade_matches_reference_traces(cubic_traces, capsys):
     """envs.CubicEnv.GridAgent (the drop-in for the reference's own scripts) with reset(seed=s): the room and start come
     from CPython's `random` exactly like the reference, so the golden traces (seeded resets) replay bit-for-bit."""
