@@ -64,6 +64,8 @@ SYMBOLS = {
     "nav3d_restore": (C.c_int, [_P, _P, C.c_size_t]),
     "nav3d_sample_actions": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, _P, _P, _P, _P]),
     "nav3d_gae": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
+    "nav3d_lstm_forward": (C.c_int, [_P] * 8 + [C.c_int32] * 5 + [_P] * 5),
+    "nav3d_lstm_backward": (C.c_int, [_P] * 8 + [C.c_int32] * 5 + [_P] * 5),
     "nav3d_launch_count": (C.c_uint64, [_P]),
     "nav3d_device_bytes": (C.c_size_t, [_P]),
 }
@@ -76,6 +78,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    try:
+        import torch  # noqa: F401  (first, so that the process uses the cuBLAS torch ships; ours binds to the same SONAME)
+    except Exception:  # noqa: BLE001
+        pass
     path = Path(os.environ.get("NAV3D_LIB", LIB_PATH))
     if not path.exists():
         raise ImportError(f"{path} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "

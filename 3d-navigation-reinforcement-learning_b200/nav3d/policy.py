@@ -69,6 +69,9 @@ class RecurrentActorCritic(nn.Module):
         self.mlp_extractor = _MlpExtractor(H, self.net_arch.get("pi", []), self.net_arch.get("vf", []))
         self.action_net = nn.Linear(self.mlp_extractor.latent_dim_pi, self.n_actions)
         self.value_net = nn.Linear(self.mlp_extractor.latent_dim_vf, 1)
+        self.two_streams = True
+        self.fused_lstm = True
+        self._streams: Dict[str, "torch.cuda.Stream"] = {}
         if ortho_init:
             for module, gain in ((self.mlp_extractor, math.sqrt(2.0)), (self.action_net, 0.01), (self.value_net, 1.0)):
                 for m in module.modules():
@@ -93,10 +96,19 @@ class RecurrentActorCritic(nn.Module):
         keep = (1.0 - starts.to(state[0].dtype)).view(1, -1, 1)
         return state[0] * keep, state[1] * keep
 
-    @staticmethod
-    def _run_lstm(lstm: nn.LSTM, x: torch.Tensor, state, starts: torch.Tensor, cuts: Sequence[int]):
+    def _run_lstm(self, lstm: nn.LSTM, x: torch.Tensor, state, starts: torch.Tensor, cuts: Sequence[int]):
         """x [S,B,F], starts [S,B] (1 = the state entering step t is zeroed), cuts = sorted timesteps at which a mask
-        has to be applied (0 is always one).  Between cuts the fused cuDNN sequence kernel runs."""
+        has to be applied (0 is always one).
+
+        Sequences on a CUDA device go through the library's fused LSTM (``nav3d_lstm_forward/backward``: the episode-start
+        mask is an operand, so nothing is cut, and the backward avoids cuDNN's bulk gate-gradient pass — DESIGN.md §6b).
+        Single steps and CPU tensors use torch's LSTM, run over every stretch between cuts."""
+        if (self.fused_lstm and x.is_cuda and x.shape[0] > 1 and lstm.num_layers == 1 and x.dtype == torch.float32
+                and not torch.cuda.is_current_stream_capturing()):
+            from .train_ops import fused_lstm
+            y, h, c = fused_lstm(x, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, state[0][0],
+                                 state[1][0], starts)
+            return y, (h.unsqueeze(0), c.unsqueeze(0))
         outs = []
         S = x.shape[0]
         cuts = list(cuts)
@@ -107,29 +119,50 @@ class RecurrentActorCritic(nn.Module):
             outs.append(y)
         return (outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)), state
 
-    def _latents(self, obs: torch.Tensor, state: LSTMState, starts: torch.Tensor, cuts: Sequence[int]):
-        h_pi, c_pi, h_vf, c_vf = state
-        lat_pi, (h_pi, c_pi) = self._run_lstm(self.lstm_actor, obs, (h_pi, c_pi), starts, cuts)
-        if self.lstm_critic is not None:
-            lat_vf, (h_vf, c_vf) = self._run_lstm(self.lstm_critic, obs, (h_vf, c_vf), starts, cuts)
-        elif self.shared_lstm:
-            lat_vf = lat_pi.detach()
-            h_vf, c_vf = h_pi.detach(), c_pi.detach()
-        else:
-            lat_vf = self.critic(obs)
-        return lat_pi, lat_vf, (h_pi, c_pi, h_vf, c_vf)
-
     # ---- forward passes ----------------------------------------------------------------------------------------
+    def _critic_branch(self, obs, h_vf, c_vf, starts, cuts):
+        lat_vf, (h_vf, c_vf) = self._run_lstm(self.lstm_critic, obs, (h_vf, c_vf), starts, cuts)
+        return self.value_net(self.mlp_extractor.value_net(lat_vf)).squeeze(-1), h_vf, c_vf
+
     def forward_sequence(self, obs: torch.Tensor, state: LSTMState, starts: torch.Tensor,
                          cuts: Optional[Sequence[int]] = None):
         """obs [S,B,F], starts [S,B] -> logits [S,B,A], values [S,B], final state.  ``cuts=None`` = mask at every step
-        (always correct); pass the timesteps that can hold an episode start to let cuDNN run whole stretches."""
+        (always correct); pass the timesteps that can hold an episode start to let cuDNN run whole stretches.
+
+        With a separate critic LSTM on a CUDA device the critic branch (LSTM + value MLP) runs on a second stream: the two
+        recurrences are independent chains of small per-timestep kernels, so running them side by side (forward, and —
+        because autograd replays each op on its forward stream — backward too) hides one chain behind the other."""
         if cuts is None:
             cuts = range(obs.shape[0])
-        lat_pi, lat_vf, state = self._latents(obs, state, starts, cuts)
+        h_pi, c_pi, h_vf, c_vf = state
+        side = None
+        if self.lstm_critic is not None and obs.is_cuda and self.two_streams and not torch.cuda.is_current_stream_capturing():
+            main = torch.cuda.current_stream(obs.device)
+            side = self._side_stream(obs.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                values, h_vf, c_vf = self._critic_branch(obs, h_vf, c_vf, starts, cuts)
+        elif self.lstm_critic is not None:
+            values, h_vf, c_vf = self._critic_branch(obs, h_vf, c_vf, starts, cuts)
+        lat_pi, (h_pi, c_pi) = self._run_lstm(self.lstm_actor, obs, (h_pi, c_pi), starts, cuts)
         logits = self.action_net(self.mlp_extractor.policy_net(lat_pi))
-        values = self.value_net(self.mlp_extractor.value_net(lat_vf)).squeeze(-1)
-        return logits, values, state
+        if side is not None:
+            main.wait_stream(side)
+            for t in (values, h_vf, c_vf):
+                t.record_stream(main)               # allocated on the side stream, consumed on the main one
+        elif self.lstm_critic is None:
+            if self.shared_lstm:
+                lat_vf, h_vf, c_vf = lat_pi.detach(), h_pi.detach(), c_pi.detach()
+            else:
+                lat_vf = self.critic(obs)
+            values = self.value_net(self.mlp_extractor.value_net(lat_vf)).squeeze(-1)
+        return logits, values, (h_pi, c_pi, h_vf, c_vf)
+
+    def _side_stream(self, device):
+        key = str(device)
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=device)
+        return self._streams[key]
 
     def forward_step(self, obs: torch.Tensor, state: LSTMState, starts: torch.Tensor):
         """One timestep: obs [B,F], starts [B] -> logits [B,A], values [B], new state."""

@@ -72,3 +72,62 @@ class DeviceOps:
             check(self._lib.nav3d_gae(_ptr(rewards), _ptr(values), _ptr(episode_starts), _ptr(last_values),
                                       _ptr(last_dones), float(gamma), float(gae_lambda), T, N, _ptr(advantages),
                                       _ptr(returns), _stream(dev)))
+
+
+class _FusedLSTMFn(torch.autograd.Function):
+    """``nav3d_lstm_forward`` / ``nav3d_lstm_backward`` as one autograd node: (x, w_ih, w_hh, b_ih, b_hh, h0, c0, starts)
+    -> (h_all, h_last, c_last).  Gradients flow to the four parameters only (see include/nav3d.h)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, h0, c0, starts, tf32):
+        lib = _lib.load()
+        S, B, F = x.shape
+        H = w_hh.shape[1]
+        dev = x.device
+        x, h0, c0, starts = x.contiguous(), h0.contiguous(), c0.contiguous(), starts.contiguous()
+        w_ih_c, w_hh_c, b_ih_c, b_hh_c = w_ih.contiguous(), w_hh.contiguous(), b_ih.contiguous(), b_hh.contiguous()
+        gates = torch.empty((S, B, 4 * H), dtype=torch.float32, device=dev)
+        h_in = torch.empty((S, B, H), dtype=torch.float32, device=dev)
+        h_all = torch.empty((S, B, H), dtype=torch.float32, device=dev)
+        c_all = torch.empty((S, B, H), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.nav3d_lstm_forward(_ptr(x), _ptr(w_ih_c), _ptr(w_hh_c), _ptr(b_ih_c), _ptr(b_hh_c), _ptr(h0), _ptr(c0),
+                                         _ptr(starts), S, B, F, H, int(tf32), _ptr(gates), _ptr(h_in), _ptr(h_all),
+                                         _ptr(c_all), _stream(dev)))
+        ctx.save_for_backward(x, w_hh_c, c0, starts, h_in, c_all, gates)
+        ctx.tf32 = int(tf32)
+        ctx.set_materialize_grads(False)
+        h_last, c_last = h_all[-1].clone(), c_all[-1].clone()
+        ctx.mark_non_differentiable(h_last, c_last)
+        return h_all, h_last, c_last
+
+    @staticmethod
+    def backward(ctx, dh_all, _dh_last, _dc_last):
+        if dh_all is None:
+            return (None,) * 9
+        lib = _lib.load()
+        x, w_hh, c0, starts, h_in, c_all, gates = ctx.saved_tensors
+        S, B, F = x.shape
+        H = w_hh.shape[1]
+        dev = x.device
+        dh_all = dh_all.contiguous()
+        dw_ih = torch.empty((4 * H, F), dtype=torch.float32, device=dev)
+        dw_hh = torch.empty((4 * H, H), dtype=torch.float32, device=dev)
+        db = torch.empty(4 * H, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2 * B * H + S * B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            # `gates` is consumed (overwritten with the pre-activation gradients): this node can be differentiated once
+            check(lib.nav3d_lstm_backward(_ptr(x), _ptr(w_hh), _ptr(c0), _ptr(starts), _ptr(h_in), _ptr(c_all), _ptr(gates),
+                                          _ptr(dh_all), S, B, F, H, ctx.tf32, _ptr(dw_ih), _ptr(dw_hh), _ptr(db),
+                                          _ptr(scratch), _stream(dev)))
+        return None, dw_ih, dw_hh, db, db, None, None, None, None
+
+
+def fused_lstm(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh, h0, c0, starts: torch.Tensor, tf32: Optional[bool] = None):
+    """x f32 [S,B,F], h0/c0 f32 [B,H], starts u8 [S,B] -> (h_all [S,B,H], h_last [B,H], c_last [B,H])."""
+    _need_cuda(x, w_ih, w_hh, h0, c0, starts)
+    if x.dtype != torch.float32 or starts.dtype != torch.uint8:
+        raise ValueError("fused_lstm: x must be float32 and starts uint8")
+    if tf32 is None:
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+    return _FusedLSTMFn.apply(x, w_ih, w_hh, b_ih, b_hh, h0, c0, starts, bool(tf32))

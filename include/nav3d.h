@@ -187,6 +187,25 @@ int nav3d_gae(const float *rewards, const float *values, const uint8_t *episode_
               const uint8_t *last_dones, float gamma, float gae_lambda, int32_t T, int32_t n, float *advantages,
               float *returns, void *stream);
 
+/* One-layer LSTM over a sequence minibatch with episode-start resets (the PPO update's recurrent pass).  Replaces the
+ * `nn.LSTM` calls of sb3-contrib's RecurrentActorCriticPolicy._process_sequence inside RecurrentPPO.train()
+ * (train/Grid_Train.py:228), which cut the sequence at every reset.  torch weight layout: w_ih f32[4H][F], w_hh f32[4H][H],
+ * b_ih, b_hh f32[4H], gate order i,f,g,o.  Row-major, time-major buffers; the recurrent GEMMs are cuBLAS calls
+ * (tf32 != 0: TF32 tensor-op math), everything else one fused kernel per timestep.
+ *   x f32[S][B][F]; h0, c0 f32[B][H]; starts u8[S][B] (1 = the state entering step t is zeroed)
+ *   out: gates f32[S][B][4H] (activated i,f,g,o, kept for backward), h_in f32[S][B][H] (masked state entering each step),
+ *        h_all, c_all f32[S][B][H] (h_all is the layer output; the final state is row S-1 of h_all / c_all) */
+int nav3d_lstm_forward(const float *x, const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh,
+                       const float *h0, const float *c0, const uint8_t *starts, int32_t S, int32_t B, int32_t F, int32_t H,
+                       int32_t tf32, float *gates, float *h_in, float *h_all, float *c_all, void *stream);
+/* Backward of the above for a loss that depends on h_all only: dh_all f32[S][B][H] in; `gates` is overwritten with the
+ * gradients w.r.t. the gate pre-activations; out dw_ih f32[4H][F], dw_hh f32[4H][H], db f32[4H] (gradient of b_ih and of
+ * b_hh alike).  scratch: f32[2*B*H + S*B].  No gradient is produced for x, h0 or c0 (observations and carried states are
+ * constants of the PPO update). */
+int nav3d_lstm_backward(const float *x, const float *w_hh, const float *c0, const uint8_t *starts, const float *h_in,
+                        const float *c_all, float *gates, const float *dh_all, int32_t S, int32_t B, int32_t F, int32_t H,
+                        int32_t tf32, float *dw_ih, float *dw_hh, float *db, float *scratch, void *stream);
+
 /* Number of CUDA kernels this library has launched since the engine was created (bench.py's gpu_launches). */
 uint64_t nav3d_launch_count(const nav3d_engine *e);
 /* Bytes of device memory the engine holds. */

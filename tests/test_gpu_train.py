@@ -118,3 +118,78 @@ def test_ppo_learns_on_gpu_env(tmp_path):
     assert torch.equal(a1, a2)
     st = evaluate_policy(again, eval_env, n_eval_episodes=8, return_episode_stats=True)
     assert len(st["r"]) == 8 and (st["total_free"] == 144).all()
+
+
+@pytest.mark.parametrize("S,B,F,H,p_start", [(1, 3, 5, 8, 0.5), (17, 33, 80, 64, 0.15), (128, 512, 80, 256, 0.01), (64, 700, 80, 256, 0.0)])
+def test_fused_lstm_matches_torch_lstm(S, B, F, H, p_start):
+    """nav3d_lstm_forward / nav3d_lstm_backward against torch.nn.LSTM stepped one timestep at a time with the state
+    zeroed at episode starts (plain fp32, TF32 off on both sides): outputs, final state and all four parameter gradients.
+    Tolerance: 2e-5 absolute on outputs in [-1, 1], 1e-4 relative to each gradient's largest entry (fp32 sums over up to
+    65 536 rows in a different order)."""
+    from nav3d.train_ops import fused_lstm
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator(device="cuda").manual_seed(S * 7 + B)
+        lstm = torch.nn.LSTM(F, H).cuda()
+        x = torch.randn((S, B, F), generator=g, device="cuda")
+        h0 = torch.randn((B, H), generator=g, device="cuda") * 0.5
+        c0 = torch.randn((B, H), generator=g, device="cuda") * 0.5
+        starts = (torch.rand((S, B), generator=g, device="cuda") < p_start).to(torch.uint8)
+        wgt = torch.randn((S, B, H), generator=g, device="cuda")
+        # reference
+        st = (h0.unsqueeze(0), c0.unsqueeze(0))
+        outs = []
+        for t in range(S):
+            keep = (1.0 - starts[t].float()).view(1, B, 1)
+            y, st = lstm(x[t:t + 1], (st[0] * keep, st[1] * keep))
+            outs.append(y)
+        ref = torch.cat(outs)
+        lstm.zero_grad()
+        (ref * wgt).sum().backward()
+        ref_grads = [p.grad.clone() for p in lstm.parameters()]
+        # fused
+        lstm.zero_grad()
+        y, h_last, c_last = fused_lstm(x, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, h0, c0, starts, tf32=False)
+        assert (y - ref.detach()).abs().max().item() < 2e-5
+        assert (h_last - st[0][0].detach()).abs().max().item() < 2e-5 and (c_last - st[1][0].detach()).abs().max().item() < 5e-5
+        (y * wgt).sum().backward()
+        for p, r in zip(lstm.parameters(), ref_grads):
+            assert (p.grad - r).abs().max().item() <= 1e-4 * (r.abs().max().item() + 1e-6), (p.shape, (p.grad - r).abs().max().item(), r.abs().max().item())
+        # TF32 tensor-op math for the GEMMs: same function to TF32 accuracy
+        y32, _, _ = fused_lstm(x, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, h0, c0, starts, tf32=True)
+        assert (y32 - ref.detach()).abs().max().item() < 2e-2
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_policy_fused_and_cudnn_paths_agree():
+    """RecurrentActorCritic.forward_sequence through the fused LSTM (default on CUDA) and through cuDNN with cuts, and with
+    the critic branch on its own stream or not: same logits/values and the same gradients (TF32 off)."""
+    from nav3d.policy import RecurrentActorCritic
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        pol = RecurrentActorCritic(net_arch=dict(pi=[256, 256, 128], vf=[256, 256, 128]), lstm_hidden_size=256).cuda()
+        S, B = 32, 96
+        obs = torch.rand((S, B, 80), device="cuda")
+        starts = (torch.rand((S, B), device="cuda") < 0.05).to(torch.uint8)
+        state = tuple(0.3 * torch.randn((1, B, 256), device="cuda") for _ in range(4))
+        cuts = [0] + [t for t in range(1, S) if bool(starts[t].any())]
+        results = []
+        for fused, two in ((False, False), (True, False), (True, True), (False, True)):
+            pol.fused_lstm, pol.two_streams = fused, two
+            pol.zero_grad()
+            logits, values, st = pol.forward_sequence(obs, state, starts, cuts)
+            (logits.square().mean() + values.square().mean()).backward()
+            torch.cuda.synchronize()
+            results.append((logits.detach(), values.detach(), [s.detach() for s in st], [p.grad.clone() for p in pol.parameters()]))
+        base = results[0]
+        for r in results[1:]:
+            assert torch.allclose(r[0], base[0], atol=1e-5) and torch.allclose(r[1], base[1], atol=1e-5)
+            assert all(torch.allclose(a, b, atol=5e-5) for a, b in zip(r[2], base[2]))
+            for a, b in zip(r[3], base[3]):
+                assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-6)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
