@@ -95,9 +95,22 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(float *__restrict__ 
     dc_rec[idx] = dc * f * keep;
 }
 
-__global__ void __launch_bounds__(256) fill_ones_kernel(float *p, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 1.f;
+// db[c] = sum over rows of dG[row][c].  grid.x tiles the 4H columns (one thread per column: coalesced row reads),
+// grid.y splits the rows; partial sums meet in db with one atomicAdd per thread (db zeroed beforehand).
+__global__ void __launch_bounds__(256) column_sum_kernel(const float *__restrict__ dg, long long rows, int cols,
+                                                         float *__restrict__ db) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long long per = (rows + gridDim.y - 1) / gridDim.y;
+    const long long r0 = (long long)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    long long r = r0;
+    for (; r + 3 < r1; r += 4) {
+        acc0 += dg[r * cols + c]; acc1 += dg[(r + 1) * cols + c];
+        acc2 += dg[(r + 2) * cols + c]; acc3 += dg[(r + 3) * cols + c];
+    }
+    for (; r < r1; r++) acc0 += dg[r * cols + c];
+    atomicAdd(db + c, (acc0 + acc1) + (acc2 + acc3));
 }
 
 std::mutex g_handle_mu;
@@ -181,7 +194,7 @@ int nav3d_lstm_backward(const float *x, const float *w_hh, const float *c0, cons
     const float one = 1.f, zero = 0.f;
     const long long SB = (long long)S * B, BH = (long long)B * H;
     const int G4 = 4 * H;
-    float *dh_rec = scratch, *dc_rec = scratch + BH, *ones = scratch + 2 * BH;     // scratch: 2*B*H + S*B floats
+    float *dh_rec = scratch, *dc_rec = scratch + BH;                               // scratch: 2*B*H floats (+ S*B unused)
     for (int t = S - 1; t >= 0; t--) {
         float *g_t = gates + (size_t)t * B * G4;
         const float *c_prev = t == 0 ? c0 : c_all + (size_t)(t - 1) * BH;
@@ -195,8 +208,13 @@ int nav3d_lstm_backward(const float *x, const float *w_hh, const float *c0, cons
     // weight gradients over the whole sequence: dW_hh[4H, H] = dG^T @ h_in, dW_ih[4H, F] = dG^T @ x, db = column sums of dG
     CUBLAS_TRY(cublasSgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_T, H, G4, (int)SB, &one, h_in, H, gates, G4, &zero, dw_hh, H));
     CUBLAS_TRY(cublasSgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_T, F, G4, (int)SB, &one, x, F, gates, G4, &zero, dw_ih, F));
-    fill_ones_kernel<<<blocks_for(SB), 256, 0, s>>>(ones, SB);
-    CUBLAS_TRY(cublasSgemv(hnd, CUBLAS_OP_N, G4, (int)SB, &one, gates, G4, ones, 1, &zero, db, 1));
+    if (cudaMemsetAsync(db, 0, sizeof(float) * G4, s) != cudaSuccess)
+        return nav3d::fail_with(NAV3D_ERR_CUDA, "nav3d_lstm_backward: cudaMemsetAsync failed");
+    {
+        const unsigned gx = (unsigned)((G4 + 255) / 256);
+        const unsigned gy = (unsigned)(SB < 592 ? SB : 592);       // 148 SMs x 4 row slabs per column tile
+        column_sum_kernel<<<dim3(gx, gy), 256, 0, s>>>(gates, SB, G4, db);
+    }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nav3d::fail_with(NAV3D_ERR_CUDA, std::string("nav3d_lstm_backward: ") + cudaGetErrorString(err));
     return NAV3D_OK;

@@ -23,7 +23,8 @@ constexpr uint32_t kStreamPolicy = 0x504f4c49u;   // "POLI": counter = (global_e
 // log pi(a|s) and the entropy, so the rollout needs no second softmax.
 template <bool GREEDY>
 __global__ void __launch_bounds__(256) sample_actions_kernel(const float *__restrict__ logits, int N, int A,
-                                                             uint32_t env_id0, uint32_t step, uint32_t seed_lo,
+                                                             uint32_t env_id0, uint32_t step,
+                                                             const uint32_t *__restrict__ step_offset, uint32_t seed_lo,
                                                              uint32_t seed_hi, long long *__restrict__ actions,
                                                              float *__restrict__ log_prob, float *__restrict__ entropy) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,7 +42,9 @@ __global__ void __launch_bounds__(256) sample_actions_kernel(const float *__rest
     int a = arg;
     if (!GREEDY) {
         uint32_t u0, u1;
-        philox4x32_10(env_id0 + (uint32_t)n, step, 0u, kStreamPolicy, seed_lo, seed_hi, u0, u1);
+        // step_offset lives in device memory so that a CUDA graph of a whole rollout can be replayed with fresh draws
+        const uint32_t idx = step + (step_offset ? *step_offset : 0u);
+        philox4x32_10(env_id0 + (uint32_t)n, idx, 0u, kStreamPolicy, seed_lo, seed_hi, u0, u1);
         const float target = (float)u0 * (1.0f / 4294967296.0f) * sum;       // u in [0, 1)
         float acc = 0.f;
         a = A - 1;
@@ -96,7 +99,8 @@ static int train_fail(int code, const std::string &msg) { return nav3d::fail_wit
 extern "C" {
 
 int nav3d_sample_actions(const float *logits, int32_t n, int32_t n_actions, uint64_t seed, uint32_t env_id0,
-                         uint32_t step, int32_t greedy, int64_t *actions, float *log_prob, float *entropy, void *stream) {
+                         uint32_t step, const uint32_t *step_offset, int32_t greedy, int64_t *actions, float *log_prob,
+                         float *entropy, void *stream) {
     if (!logits || !actions) return train_fail(NAV3D_ERR_INVALID, "logits and actions are required");
     if (n < 0 || n_actions < 1 || n_actions > 1024) return train_fail(NAV3D_ERR_INVALID, "bad n / n_actions");
     if (n == 0) return NAV3D_OK;
@@ -104,10 +108,10 @@ int nav3d_sample_actions(const float *logits, int32_t n, int32_t n_actions, uint
     const unsigned grid = (unsigned)((n + 255) / 256);
     long long *a = reinterpret_cast<long long *>(actions);
     if (greedy)
-        sample_actions_kernel<true><<<grid, 256, 0, s>>>(logits, n, n_actions, env_id0, step, (uint32_t)seed,
+        sample_actions_kernel<true><<<grid, 256, 0, s>>>(logits, n, n_actions, env_id0, step, step_offset, (uint32_t)seed,
                                                          (uint32_t)(seed >> 32), a, log_prob, entropy);
     else
-        sample_actions_kernel<false><<<grid, 256, 0, s>>>(logits, n, n_actions, env_id0, step, (uint32_t)seed,
+        sample_actions_kernel<false><<<grid, 256, 0, s>>>(logits, n, n_actions, env_id0, step, step_offset, (uint32_t)seed,
                                                           (uint32_t)(seed >> 32), a, log_prob, entropy);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return train_fail(NAV3D_ERR_CUDA, std::string("nav3d_sample_actions: ") + cudaGetErrorString(err));

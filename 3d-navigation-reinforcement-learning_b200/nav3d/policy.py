@@ -139,6 +139,8 @@ class RecurrentActorCritic(nn.Module):
         if self.lstm_critic is not None and obs.is_cuda and self.two_streams and not torch.cuda.is_current_stream_capturing():
             main = torch.cuda.current_stream(obs.device)
             side = self._side_stream(obs.device)
+            # the critic's parameters accumulate their gradients on the side stream by design
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 values, h_vf, c_vf = self._critic_branch(obs, h_vf, c_vf, starts, cuts)

@@ -50,7 +50,8 @@ class RecurrentPPO:
                  batch_size: int = 128, n_epochs: int = 10, gamma: float = 0.99, gae_lambda: float = 0.95,
                  clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  normalize_advantage: bool = True, seq_len: Optional[int] = None, seed: Optional[int] = 0,
-                 verbose: int = 0, ops=None, device=None, policy: str = "MlpLstmPolicy", allow_tf32: bool = True):
+                 verbose: int = 0, ops=None, device=None, policy: str = "MlpLstmPolicy", allow_tf32: bool = True,
+                 cuda_graph: bool = True):
         if policy != "MlpLstmPolicy":
             raise ValueError("only MlpLstmPolicy is implemented (the one the reference trains)")
         self.policy_kwargs = dict(policy_kwargs or {})
@@ -59,6 +60,7 @@ class RecurrentPPO:
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
         self.normalize_advantage = bool(normalize_advantage)
         self.seed, self.verbose = seed, int(verbose)
+        self.cuda_graph = bool(cuda_graph)
         self.num_timesteps = 0
         self.n_updates = 0
         self._iteration = 0
@@ -132,53 +134,108 @@ class RecurrentPPO:
         self._last_starts = torch.ones(N, dtype=torch.uint8, device=dev)
         self._obs[0].copy_(env.reset())
         self._carry_obs = False           # True once obs[T] of a finished rollout has to become obs[0] of the next
-        self._policy_step = 0
+        self._graph = None                # CUDA graph of one whole rollout (captured at the second rollout)
+        # Philox policy-stream position: a device counter (so a captured rollout draws fresh numbers on replay)
+        self._step_base = torch.zeros(1, dtype=torch.int32, device=dev) if dev.type == "cuda" else None
 
     # ---- rollout -----------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def collect_rollouts(self, callback=None) -> bool:
-        env, pol, T, S = self.env, self.policy, self.n_steps, self.seq_len
-        ep_n = torch.zeros((), dtype=torch.float32, device=self.device)
-        ep_r = torch.zeros((), dtype=torch.float32, device=self.device)
-        ep_l = torch.zeros((), dtype=torch.float32, device=self.device)
-        state, starts = self._state, self._last_starts
-        if self._carry_obs:
-            self._obs[0].copy_(self._obs[T])
-        self._carry_obs = True
-        for t in range(T):
-            if t % S == 0:
-                cs = self._chunk_states[t // S]
-                for j in range(4):
-                    cs[j].copy_(state[j])
-            self._starts[t].copy_(starts)
-            logits, values, state = pol.forward_step(self._obs[t], state, starts)
-            self._ops.sample_actions(logits, self._policy_step, False, actions=self._actions[t], log_prob=self._logp[t])
-            self._policy_step += 1
-            self._values[t].copy_(values)
-            _, reward, dones, info = env.step(self._actions[t], out_obs=self._obs[t + 1])
-            self._rewards[t].copy_(reward)
-            time_limit = (info.truncated != 0) & (info.terminated == 0)
-            if bool(time_limit.any()):
-                # bootstrap through the time limit: V(terminal_observation) with the critic state after this step
-                tv = pol.values_step(info.terminal_observation, state, torch.zeros_like(starts))
-                self._rewards[t].add_(self.gamma * tv * time_limit.to(tv.dtype))
-            dm = dones.to(torch.float32)
-            ep_n += dm.sum()
-            ep_r += (info.episodes[:, 0].view(torch.float32) * dm).sum()
-            ep_l += (info.episodes[:, 1].to(torch.float32) * dm).sum()
-            starts = dones.to(torch.uint8)
-            self.num_timesteps += self.num_envs * self.world
-            if callback is not None and callback.on_step(self) is False:
-                return False
-        last_values = pol.values_step(self._obs[T], state, starts)
+    def _rollout_step(self, t: int, state: LSTMState, starts: torch.Tensor, ep: torch.Tensor, sync_free: bool):
+        """One env step of the rollout: policy forward, sample, env step (the kernel writes obs[t+1]), time-limit
+        bootstrap, episode statistics.  ``sync_free``: no device->host read (what a CUDA-graph capture needs) — the
+        bootstrap value is then computed for every env and masked instead of only when a time limit was hit."""
+        env, pol, S = self.env, self.policy, self.seq_len
+        if t % S == 0:
+            cs = self._chunk_states[t // S]
+            for j in range(4):
+                cs[j].copy_(state[j])
+        self._starts[t].copy_(starts)
+        logits, values, state = pol.forward_step(self._obs[t], state, starts)
+        self._ops.sample_actions(logits, t, False, actions=self._actions[t], log_prob=self._logp[t],
+                                 step_offset=self._step_base)
+        self._values[t].copy_(values)
+        _, reward, dones, info = env.step(self._actions[t], out_obs=self._obs[t + 1])
+        self._rewards[t].copy_(reward)
+        time_limit = (info.truncated != 0) & (info.terminated == 0)
+        if sync_free or bool(time_limit.any()):
+            # bootstrap through the time limit: V(terminal_observation) with the critic state after this step
+            tv = pol.values_step(info.terminal_observation, state, torch.zeros_like(starts))
+            self._rewards[t].add_(self.gamma * tv * time_limit.to(tv.dtype))
+        dm = dones.to(torch.float32)
+        ep[0] += dm.sum()
+        ep[1] += (info.episodes[:, 0].view(torch.float32) * dm).sum()
+        ep[2] += (info.episodes[:, 1].to(torch.float32) * dm).sum()
+        return state, dones.to(torch.uint8)
+
+    def _finish_rollout(self, state: LSTMState, starts: torch.Tensor):
+        last_values = self.policy.values_step(self._obs[self.n_steps], state, starts)
         self._ops.gae(self._rewards, self._values, self._starts, last_values.contiguous(), starts.contiguous(),
                       self.gamma, self.gae_lambda, self._adv, self._ret)
-        self._state, self._last_starts = state, starts
-        n = float(ep_n)
+        if self._step_base is not None:
+            self._step_base.add_(self.n_steps)
+
+    @torch.no_grad()
+    def collect_rollouts(self, callback=None) -> bool:
+        """Fill the rollout buffers with ``n_steps`` env steps of every env and compute advantages/returns.
+
+        On a CUDA device, from the second rollout on, the whole rollout — n_steps x (policy forward, sampling kernel, env
+        step kernel, bootstrap, statistics) + GAE — is ONE CUDA graph replay (env and policy inference
+        fused into one launch from the host's point of view).  The first rollout runs eagerly and doubles as the warm-up
+        that graph capture needs.  Callbacks are then stepped after the replay; the policy does not change inside a
+        rollout, so an evaluation triggered by them sees the same policy as it would have mid-rollout."""
+        T = self.n_steps
+        use_graph = self.cuda_graph and self.device.type == "cuda" and self._carry_obs
+        if use_graph and self._graph is None:
+            try:
+                self._capture_rollout_graph()
+            except Exception as ex:  # noqa: BLE001
+                self.cuda_graph = False
+                use_graph = False
+                if self.verbose:
+                    print(f"CUDA-graph capture of the rollout failed ({ex!r}); continuing with eager launches")
+        if use_graph:
+            self._graph.replay()
+            for _ in range(T):
+                self.num_timesteps += self.num_envs * self.world
+                if callback is not None and callback.on_step(self) is False:
+                    return False
+            ep = self._g_ep
+        else:
+            ep = torch.zeros(3, dtype=torch.float32, device=self.device)
+            state, starts = self._state, self._last_starts
+            if self._carry_obs:
+                self._obs[0].copy_(self._obs[T])
+            self._carry_obs = True
+            for t in range(T):
+                state, starts = self._rollout_step(t, state, starts, ep, sync_free=False)
+                self.num_timesteps += self.num_envs * self.world
+                if callback is not None and callback.on_step(self) is False:
+                    return False
+            self._finish_rollout(state, starts)
+            for j in range(4):
+                self._state[j].copy_(state[j])
+            self._last_starts.copy_(starts)
+        n, r, l = ep.cpu().tolist()
         if n > 0:
-            self._ep_return_mean, self._ep_len_mean = float(ep_r) / n, float(ep_l) / n
+            self._ep_return_mean, self._ep_len_mean = r / n, l / n
         self._episodes_this_rollout = int(n)
         return True
+
+    def _capture_rollout_graph(self):
+        T = self.n_steps
+        self._g_ep = torch.zeros(3, dtype=torch.float32, device=self.device)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(graph):
+            self._g_ep.zero_()
+            self._obs[0].copy_(self._obs[T])
+            state, starts = self._state, self._last_starts
+            for t in range(T):
+                state, starts = self._rollout_step(t, state, starts, self._g_ep, sync_free=True)
+            self._finish_rollout(state, starts)
+            for j in range(4):
+                self._state[j].copy_(state[j])
+            self._last_starts.copy_(starts)
+        self._graph = graph
 
     # ---- update ------------------------------------------------------------------------------------------------
     def _chunk_view(self, x: torch.Tensor) -> torch.Tensor:

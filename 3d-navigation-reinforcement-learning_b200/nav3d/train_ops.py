@@ -37,8 +37,10 @@ class DeviceOps:
 
     def sample_actions(self, logits: torch.Tensor, step: int, greedy: bool = False,
                        actions: Optional[torch.Tensor] = None, log_prob: Optional[torch.Tensor] = None,
-                       entropy: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """logits f32 [N, A] -> (actions int64 [N], log_prob f32 [N]); ``step`` indexes the env's Philox policy stream."""
+                       entropy: Optional[torch.Tensor] = None,
+                       step_offset: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """logits f32 [N, A] -> (actions int64 [N], log_prob f32 [N]); ``step`` (+ the int32 device scalar ``step_offset``,
+        read by the kernel) indexes the env's Philox policy stream."""
         _need_cuda(logits)
         if logits.dtype != torch.float32 or logits.dim() != 2:
             raise ValueError("logits must be a float32 [N, A] tensor")
@@ -50,9 +52,11 @@ class DeviceOps:
         if log_prob is None:
             log_prob = torch.empty(n, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            if step_offset is not None and (step_offset.dtype != torch.int32 or step_offset.numel() != 1 or not step_offset.is_cuda):
+                raise ValueError("step_offset must be a CUDA int32 tensor with one element")
             check(self._lib.nav3d_sample_actions(_ptr(logits), n, a, self.seed, self.env_id0, int(step) & 0xFFFFFFFF,
-                                                 int(bool(greedy)), _ptr(actions), _ptr(log_prob), _ptr(entropy),
-                                                 _stream(dev)))
+                                                 _ptr(step_offset), int(bool(greedy)), _ptr(actions), _ptr(log_prob),
+                                                 _ptr(entropy), _stream(dev)))
         return actions, log_prob
 
     def gae(self, rewards: torch.Tensor, values: torch.Tensor, episode_starts: torch.Tensor, last_values: torch.Tensor,

@@ -264,7 +264,8 @@ def time_training(torch, dist, world, rank, local_rank, n_envs=4096, n_steps=128
                                                  n_lstm_layers=1),
                          learning_rate=3e-4, n_steps=n_steps, batch_size=512 * n_steps, n_epochs=10, gamma=0.99,
                          gae_lambda=0.95, ent_coef=0.01, vf_coef=0.5, clip_range=0.2, seed=42)
-    model.collect_rollouts(); model.train()
+    for _ in range(2):                  # warm-up: one eager rollout, then the CUDA-graph capture of the rollout
+        model.collect_rollouts(); model.train()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

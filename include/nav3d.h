@@ -173,11 +173,14 @@ int nav3d_restore(nav3d_engine *e, const void *host_buf, size_t bytes);
  * `distribution.get_actions()/log_prob()` and `RecurrentRolloutBuffer.compute_returns_and_advantage`. ---- */
 
 /* Categorical sampling from policy logits f32[n][n_actions] (row-major).  u = word 0 of Philox4x32-10 with
- * counter = (env_id0 + i, step, 0, 0x504f4c49) and the key of `seed`; action = first k with cumsum(softmax)[k] > u.
+ * counter = (env_id0 + i, step + *step_offset, 0, 0x504f4c49) and the key of `seed`; action = first k with
+ * cumsum(softmax)[k] > u.  step_offset: DEVICE u32[1] or NULL (= 0) — a counter in device memory, so that a CUDA graph
+ * that captured a whole rollout draws fresh numbers on every replay.
  * greedy != 0: argmax instead (SB3's deterministic=True, train/evaluate_grid.py:186-191).
  *   actions : int64[n] (directly usable by nav3d_step)   log_prob : f32[n] or NULL   entropy : f32[n] or NULL */
 int nav3d_sample_actions(const float *logits, int32_t n, int32_t n_actions, uint64_t seed, uint32_t env_id0,
-                         uint32_t step, int32_t greedy, int64_t *actions, float *log_prob, float *entropy, void *stream);
+                         uint32_t step, const uint32_t *step_offset, int32_t greedy, int64_t *actions, float *log_prob,
+                         float *entropy, void *stream);
 
 /* GAE(lambda) over a time-major rollout: rewards, values f32[T][n]; episode_starts u8[T][n] (1 = step t is the first of
  * an episode); last_values f32[n] = V(s_T); last_dones u8[n] = the episode ended at step T-1.

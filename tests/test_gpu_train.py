@@ -104,7 +104,7 @@ def test_ppo_learns_on_gpu_env(tmp_path):
     launches0 = env.engine.launch_count
     model.learn(total_timesteps=iters * 64 * 256, callback=cb)
     assert model.num_timesteps == iters * 64 * 256 and len(model.logger) == iters
-    assert env.engine.launch_count - launches0 >= iters * 64       # every rollout step is a nav3d_step launch
+    assert env.engine.launch_count - launches0 >= 2 * 64           # host-side launches: the eager rollout + the capture; later rollouts are graph replays
     for rec in model.logger:
         assert all(math.isfinite(rec[k]) for k in ("loss", "policy_loss", "value_loss", "entropy_loss", "approx_kl"))
     curve = [r["ep_rew_mean"] for r in model.logger if math.isfinite(r["ep_rew_mean"])]
@@ -193,3 +193,42 @@ def test_policy_fused_and_cudnn_paths_agree():
                 assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-6)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_cuda_graph_rollout_equals_eager_rollout():
+    """From the second rollout on, collect_rollouts replays ONE CUDA graph of the whole rollout; it must fill the buffers
+    exactly like the eager loop (same Philox draws through the device-side step counter, same env steps, same GAE)."""
+    from nav3d import BatchedCubicEnv
+    from nav3d.ppo import RecurrentPPO
+    from nav3d.rooms import load_room_file
+    # 149- and 302-step episodes: resets and time limits fall inside every rollout after the first
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt"), load_room_file(ROOMS / "P2_training" / "tightcorridor.txt")]
+    models = []
+    for graph in (False, True):
+        env = BatchedCubicEnv(rooms=rooms, num_envs=192, local_map_length=10, seed=5)
+        m = RecurrentPPO(env, policy_kwargs=dict(net_arch=dict(pi=[64, 64], vf=[64, 64]), lstm_hidden_size=64), n_steps=96,
+                         batch_size=96 * 64, n_epochs=1, seed=3, cuda_graph=graph)
+        models.append(m)
+    calls = [0, 0]
+
+    class Count:
+        def __init__(self, i): self.i = i
+        def on_step(self, model):
+            calls[self.i] += 1
+            return True
+    for r in range(4):
+        for i, m in enumerate(models):
+            assert m.collect_rollouts(Count(i))
+        a, b = models
+        assert (b._graph is not None) == (r >= 1) and a._graph is None
+        assert torch.equal(a._actions, b._actions) and torch.equal(a._obs, b._obs) and torch.equal(a._starts, b._starts)
+        assert torch.allclose(a._rewards, b._rewards, atol=1e-5) and torch.allclose(a._values, b._values, atol=1e-5)
+        assert torch.allclose(a._adv, b._adv, atol=1e-4) and torch.allclose(a._logp, b._logp, atol=1e-5)
+        assert torch.allclose(a._chunk_states, b._chunk_states, atol=1e-5)
+        assert a.num_timesteps == b.num_timesteps == (r + 1) * 96 * 192 and calls[0] == calls[1] == (r + 1) * 96
+        assert a._episodes_this_rollout == b._episodes_this_rollout
+        assert (math.isnan(a._ep_return_mean) and math.isnan(b._ep_return_mean)) or abs(a._ep_return_mean - b._ep_return_mean) < 1e-3
+    assert int(a._starts.sum()) > 0 and a._episodes_this_rollout > 0
+    # training between graph replays keeps working (the graph reads the parameters in place)
+    b.train()
+    assert b.collect_rollouts()

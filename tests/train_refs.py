@@ -29,7 +29,7 @@ class TorchOps:
     def __init__(self, seed=0):
         self.gen = torch.Generator().manual_seed(seed)
 
-    def sample_actions(self, logits, step, greedy=False, actions=None, log_prob=None, entropy=None):
+    def sample_actions(self, logits, step, greedy=False, actions=None, log_prob=None, entropy=None, step_offset=None):
         lp = torch.log_softmax(logits, dim=-1)
         a = lp.argmax(-1) if greedy else torch.multinomial(lp.exp().cpu(), 1, generator=self.gen).squeeze(-1).to(logits.device)
         l = lp.gather(-1, a.unsqueeze(-1)).squeeze(-1)

@@ -31,7 +31,8 @@ def main():
                      learning_rate=3e-4, n_steps=args.n_steps, batch_size=args.batch_envs * args.n_steps, n_epochs=args.epochs,
                      gamma=0.99, gae_lambda=0.95, ent_coef=0.01, vf_coef=0.5, clip_range=0.2, seed=0)
     m.policy.two_streams = bool(args.two_streams)
-    m.collect_rollouts(); m.train()                      # warm-up (cuDNN plans, allocator)
+    for _ in range(2):                                   # warm-up: eager rollout, then the rollout's CUDA-graph capture
+        m.collect_rollouts(); m.train()
     torch.cuda.synchronize()
     t_roll = t_train = 0.0
     for _ in range(args.iters):
