@@ -252,7 +252,7 @@ def time_e2e(eng, n, steps, torch, dist, world):
     return sec, n * 8, n * (80 * 4 + 4 + 1 + 1), checksum
 
 
-def time_training(torch, dist, world, rank, local_rank, n_envs=4096, n_steps=128, iters=3):
+def time_training(torch, dist, world, rank, local_rank, n_envs=16384, n_steps=128, iters=3):
     """BASELINE configs[4] (not roofline-graded): LSTM-PPO with the Grid_Train hyper-parameters on P1_training, env and
     rollout resident on the GPU, one rank per GPU with an NCCL gradient all-reduce per minibatch.  Weak scaling: every rank
     owns n_envs envs.  Returns env-steps/s over rollout + update, all ranks."""
@@ -262,7 +262,7 @@ def time_training(torch, dist, world, rank, local_rank, n_envs=4096, n_steps=128
                           device=local_rank, env_id0=rank * n_envs)
     model = RecurrentPPO(env, policy_kwargs=dict(net_arch=dict(pi=[256, 256, 128], vf=[256, 256, 128]), lstm_hidden_size=256,
                                                  n_lstm_layers=1),
-                         learning_rate=3e-4, n_steps=n_steps, batch_size=512 * n_steps, n_epochs=10, gamma=0.99,
+                         learning_rate=3e-4, n_steps=n_steps, batch_size=(n_envs // 8) * n_steps, n_epochs=10, gamma=0.99,
                          gae_lambda=0.95, ent_coef=0.01, vf_coef=0.5, clip_range=0.2, seed=42)
     for _ in range(2):                  # warm-up: one eager rollout, then the CUDA-graph capture of the rollout
         model.collect_rollouts(); model.train()
@@ -282,7 +282,7 @@ def time_training(torch, dist, world, rank, local_rank, n_envs=4096, n_steps=128
         sec = float(tmax.item())
     steps = iters * n_steps * n_envs * world
     out = {"workload": "BASELINE configs[4]: LSTM-PPO (MlpLstmPolicy 80->LSTM256 x2->256-256-128, Grid_Train hyper-parameters, "
-                       f"{n_envs} envs x {n_steps} steps per GPU per rollout, 512-env minibatches, 10 epochs) on P1_training, "
+                       f"{n_envs} envs x {n_steps} steps per GPU per rollout, 8 minibatches per epoch, 10 epochs) on P1_training, "
                        "GPU-resident env, NCCL gradient all-reduce per minibatch",
            "value": steps / sec, "unit": "env-steps/s (rollout + PPO update)", "iters": iters, "n_gpus": world,
            "rollout_share": t_roll / (t_roll + t_train), "rollout_steps_per_s_rank0": iters * n_steps * n_envs / t_roll,
