@@ -386,14 +386,28 @@ NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &s
 // Step 1 of get_obs (:264-266): mark every cell the six rays examined as seen.  Runs after the gather in program order
 // (the gather re-derives these bits from the ray extents) so that its stores do not fence the window loads.  The x run
 // (centre column included, which also takes the +-z cells) and the y run are handled as one index space.
+//
+// `dir` = the move that brought the agent here (0 +x, 1 -x, 2 +y, 3 -y, 4 +z, 5 -z; -1 = none: a reset).  Every cell the
+// agent has stood on had its rays marked when it was first visited, and the cell it just left lies one step back on the
+// move's axis: that cell's rays along the axis already covered everything this cell's rays cover except the single cell at
+// distance exactly L ahead.  So after a move along x (y) the x (y) run shrinks to that one far cell (if the ray reaches
+// it) — the scattered tiles of a whole run become one.
 template <int G>
-NAV3D_HD void mark_seen(const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z, const Rays &r) {
+NAV3D_HD void mark_seen(const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z, const Rays &r, int dir, int L) {
     uint16_t *__restrict__ S = reinterpret_cast<uint16_t *>(envk);
     const uint32_t zbit = 1u << z;
     const int ntx16 = R.ntx * 16;
-    const int nx = r.x1 - r.x0 + 1, total = nx + (r.y1 - r.y0 + 1);
+    int x0 = r.x0, x1 = r.x1, y0 = r.y0, y1 = r.y1, far = -1;
+    if (dir == 0) { if (x1 - x == L) far = s_index(R, x1, y); x0 = x1 = x; }
+    else if (dir == 1) { if (x - x0 == L) far = s_index(R, x0, y); x0 = x1 = x; }
+    else if (dir == 2) { if (y1 - y == L) far = s_index(R, x, y1); y0 = y1 = y; }
+    else if (dir == 3) { if (y - y0 == L) far = s_index(R, x, y0); y0 = y1 = y; }
+    const int nx = x1 - x0 + 1, total = nx + (y1 - y0 + 1);
     const int ypart = (y >> 2) * ntx16 + (y & 3), xpart = ((x >> 2) << 4) + ((x & 3) << 2);
     constexpr int RC = G >= 16 ? 2 : 4;                 // cells per lane per chunk: loads of a chunk overlap
+    uint32_t far_old = 0;
+    const bool do_far = far >= 0 && lane == G - 1;
+    if (do_far) far_old = S[far];
     for (int base = 0; base < total; base += G * RC) {
         int idx[RC];
         uint32_t old[RC], msk[RC];
@@ -403,11 +417,11 @@ NAV3D_HD void mark_seen(const RoomDev &R, uint8_t *envk, int lane, int x, int y,
             int id = -1;
             msk[q] = zbit;
             if (i < nx) {
-                const int cx = r.x0 + i;
+                const int cx = x0 + i;
                 id = ((cx >> 2) << 4) + ((cx & 3) << 2) + ypart;
                 if (cx == x) msk[q] = r.zmask;
             } else if (i < total) {
-                const int cy = r.y0 + (i - nx);
+                const int cy = y0 + (i - nx);
                 if (cy != y) id = (cy >> 2) * ntx16 + (cy & 3) + xpart;       // centre column belongs to the x run
             }
             idx[q] = id;
@@ -419,6 +433,7 @@ NAV3D_HD void mark_seen(const RoomDev &R, uint8_t *envk, int lane, int x, int y,
             if (idx[q] >= 0 && n != old[q]) S[idx[q]] = (uint16_t)n;
         }
     }
+    if (do_far && (far_old | zbit) != far_old) S[far] = (uint16_t)(far_old | zbit);
 }
 
 // get_obs (CubicEnv.py:254-312) in one piece, for callers that have nothing to overlap with the window loads (reset).
@@ -435,7 +450,7 @@ NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, in
         }
         write_scalars<G>(P, lane, sc, obs_row);
     }
-    if (write_seen) mark_seen<G>(R, envk, lane, x, y, z, r);
+    if (write_seen) mark_seen<G>(R, envk, lane, x, y, z, r, -1, P.L);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -560,7 +575,7 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
     // The cells a ray pass marks depend only on the position (L and the room are fixed), and marks are never erased
     // within an episode: every earlier stay at this cell (c_old >= 1, which includes every bump) already marked
     // them.  Only a FIRST visit has anything to write, so revisits skip the ray marking and its scattered traffic.
-    if (explored && !will_reset) mark_seen<G>(R, envk, lane, x, y, z, r);
+    if (explored && !will_reset) mark_seen<G>(R, envk, lane, x, y, z, r, (int)dir, P.L);
     if (r.near_wall) flags |= kNearWall;
 
     if (lane == 0) {
