@@ -321,7 +321,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not leave the others waiting for ten minutes in a collective
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     spec = workload_spec(args.workload)
     if args.envs:
         spec["envs_total"] = args.envs
