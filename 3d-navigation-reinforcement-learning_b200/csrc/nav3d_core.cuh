@@ -642,10 +642,11 @@ NAV3D_HD uint32_t k2_bytes(const RoomDev &R) { return (uint32_t)R.ntx * R.nty * 
 NAV3D_HD int k2_code(uint32_t w, int z) { return (int)(((w >> z) & 1u) | (((w >> (16 + z)) & 1u) << 1)); }
 NAV3D_HD float k2_value(int code) { return code == 0 ? -1.0f : (float)(code - 1); }
 
-struct SimpleRay { int dx, dy, dz, nfree, blocked; bool wall; };   // blocked: a 2 is appended at step nfree+1 (wall or OOB)
-
 // get_obs (simpleEnv.py:219-265) at (x,y,z): marks the knowledge and writes the 6L+7 floats.  `centre` is the centre
 // column's word as every lane holds it (after the move's visit update); the updated word is stored by lane 0.
+// The six rays are evaluated once per absolute axis direction a (0 +x, 1 -x, 2 +y, 3 -y, 4 +z, 5 -z) and kept packed in
+// registers — free count in byte a of `nf6`, "a wall stopped it" / "a 2 is appended" in bit a of `wall6` / `blk6` — so that
+// the per-cell loop below needs no indexed local array.
 template <int G>
 NAV3D_HD void simple_observe(const EngineParams &P, const RoomDev &R, uint32_t *K, int lane, int lane_in_warp, int x, int y,
                              int z, int facing, uint32_t centre_mem, uint32_t centre, int last_action, float *obs_row) {
@@ -653,74 +654,84 @@ NAV3D_HD void simple_observe(const EngineParams &P, const RoomDev &R, uint32_t *
     const unsigned long long wx = ldg(P.occ64 + R.occx_off + (uint32_t)(y * H + z));
     const unsigned long long wy = ldg(P.occ64 + R.occy_off + (uint32_t)(x * H + z));
     const unsigned long long wz = ldg(P.occz + R.occz_off + (uint32_t)(x * D + y));
-    // order :243: forward, left, right, backward, up, down.  Headings N=+y, E=+x, S=-y, W=-x.
-    const int fx = (facing == 1) - (facing == 3), fy = (facing == 0) - (facing == 2);
-    const int lf = (facing + 3) & 3, lx = (lf == 1) - (lf == 3), ly = (lf == 0) - (lf == 2);
-    SimpleRay ray[6];
-    ray[0].dx = fx; ray[0].dy = fy; ray[0].dz = 0;
-    ray[1].dx = lx; ray[1].dy = ly; ray[1].dz = 0;
-    ray[2].dx = -lx; ray[2].dy = -ly; ray[2].dz = 0;
-    ray[3].dx = -fx; ray[3].dy = -fy; ray[3].dz = 0;
-    ray[4].dx = 0; ray[4].dy = 0; ray[4].dz = 1;
-    ray[5].dx = 0; ray[5].dy = 0; ray[5].dz = -1;
-#pragma unroll
-    for (int d = 0; d < 6; d++) {
+    unsigned long long nf6 = 0;
+    uint32_t wall6 = 0, blk6 = 0;
+    {
         int ext, nfree, near, room_left;
-        if (ray[d].dx > 0) { room_left = W - 1 - x; ray_up(wx, x, imin(L, room_left), ext, nfree, near); }
-        else if (ray[d].dx < 0) { room_left = x; ray_down(wx, x, imin(L, room_left), ext, nfree, near); }
-        else if (ray[d].dy > 0) { room_left = D - 1 - y; ray_up(wy, y, imin(L, room_left), ext, nfree, near); }
-        else if (ray[d].dy < 0) { room_left = y; ray_down(wy, y, imin(L, room_left), ext, nfree, near); }
-        else if (ray[d].dz > 0) { room_left = H - 1 - z; ray_up(wz, z, imin(L, room_left), ext, nfree, near); }
-        else { room_left = z; ray_down(wz, z, imin(L, room_left), ext, nfree, near); }
-        ray[d].nfree = nfree;
-        ray[d].wall = ext > nfree;                                   // a wall stopped the ray (:321-324)
-        ray[d].blocked = ray[d].wall || (nfree == room_left && nfree < L);   // ... or the room ended (:311-319)
+#define NAV3D_SIMPLE_RAY(a, CALL, LEFT)                                                                     \
+        room_left = (LEFT); CALL;                                                                           \
+        nf6 |= (unsigned long long)nfree << (8 * (a));                                                      \
+        wall6 |= (uint32_t)(ext > nfree) << (a);                     /* a wall stopped the ray (:321-324) */ \
+        blk6 |= (uint32_t)((ext > nfree) || (nfree == room_left && nfree < L)) << (a);   /* ... or the room ended (:311-319) */
+        NAV3D_SIMPLE_RAY(0, ray_up(wx, x, imin(L, room_left), ext, nfree, near), W - 1 - x)
+        NAV3D_SIMPLE_RAY(1, ray_down(wx, x, imin(L, room_left), ext, nfree, near), x)
+        NAV3D_SIMPLE_RAY(2, ray_up(wy, y, imin(L, room_left), ext, nfree, near), D - 1 - y)
+        NAV3D_SIMPLE_RAY(3, ray_down(wy, y, imin(L, room_left), ext, nfree, near), y)
+        NAV3D_SIMPLE_RAY(4, ray_up(wz, z, imin(L, room_left), ext, nfree, near), H - 1 - z)
+        NAV3D_SIMPLE_RAY(5, ray_down(wz, z, imin(L, room_left), ext, nfree, near), z)
+#undef NAV3D_SIMPLE_RAY
+        (void)near;
     }
     // vertical rays: all in the centre column; fold their marks into one word
-    uint32_t free_z = 0, block_z = 0;
-#pragma unroll
-    for (int d = 4; d < 6; d++) {
-        const int n = ray[d].nfree, sgn = ray[d].dz;
-        for (int s = 1; s <= n; s++) free_z |= 1u << (z + sgn * s);
-        if (ray[d].wall) block_z |= 1u << (z + sgn * (n + 1));
-        else if (ray[d].blocked && n >= 1) block_z |= 1u << (z + sgn * n);     // last in-bounds cell becomes 2 (:314-317)
-    }
+    const int nup = (int)((nf6 >> 32) & 0xff), ndn = (int)((nf6 >> 40) & 0xff);
+    uint32_t free_z = (((1u << nup) - 1u) << (z + 1)) | (((1u << ndn) - 1u) << (z - ndn));
+    uint32_t block_z = 0;
+    if (wall6 & 16u) block_z |= 1u << (z + nup + 1);
+    else if ((blk6 & 16u) && nup >= 1) block_z |= 1u << (z + nup);                 // last in-bounds cell becomes 2 (:314-317)
+    if (wall6 & 32u) block_z |= 1u << (z - ndn - 1);
+    else if ((blk6 & 32u) && ndn >= 1) block_z |= 1u << (z - ndn);
     const uint32_t lo0 = centre & 0xffffu, hi0 = centre >> 16;
     const uint32_t lo1 = lo0 | (free_z & ~hi0 & ~lo0);                           // unknown -> seen (:327-328)
     const uint32_t centre_seen = lo1 | (hi0 << 16);                              // what the ray cells report
     const uint32_t centre_new = (lo1 | block_z) | ((hi0 | block_z) << 16);
-    {
-        for (int i = lane; i < 6 * L; i += G) {
-            const int d = i / L, s = i - d * L + 1;
-            const SimpleRay rd = ray[d];
-            float v = -1.0f;                                                      // padding (:334-335)
-            if (s <= rd.nfree) {
-                const int cx = x + rd.dx * s, cy = y + rd.dy * s, cz = z + rd.dz * s;
-                if (rd.dz != 0) v = k2_value(k2_code(centre_seen, cz));
+    // ray order :243: forward, left, right, backward, up, down.  Headings N=+y, E=+x, S=-y, W=-x; heading -> axis
+    // direction index is the same nibble table the move uses (N -> 2, E -> 0, S -> 3, W -> 1).
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+        int a, dx = 0, dy = 0, dz = 0;
+        if (d < 4) {
+            const int h = (facing + ((0x2130 >> (4 * d)) & 3)) & 3;              // fwd +0, left +3, right +1, back +2
+            a = (0x1302 >> (4 * h)) & 3;
+            dx = (h == 1) - (h == 3); dy = (h == 0) - (h == 2);
+        } else { a = d; dz = (d == 4) ? 1 : -1; }
+        const int nfree = (int)((nf6 >> (8 * a)) & 0xff);
+        const bool wall = (wall6 >> a) & 1u, blocked = (blk6 >> a) & 1u;
+        for (int s = 1 + lane; s <= L; s += G) {
+            float v = -1.0f;                                                  // padding (:334-335)
+            if (s <= nfree) {
+                const int cx = x + dx * s, cy = y + dy * s, cz = z + dz * s;
+                if (d >= 4) v = k2_value(k2_code(centre_seen, cz));
                 else {
                     uint32_t *p = K + s_index(R, cx, cy);
                     uint32_t w = *p, n = w;
                     int code = k2_code(w, cz);
-                    if (code == 0) { code = 1; n |= 1u << cz; }                   // -1 -> 0
+                    if (code == 0) { code = 1; n |= 1u << cz; }               // -1 -> 0
                     v = k2_value(code);
-                    if (s == rd.nfree && rd.blocked && !rd.wall) n |= (1u << cz) | (1u << (16 + cz));   // then becomes 2
+                    if (s == nfree && blocked && !wall) n |= (1u << cz) | (1u << (16 + cz));   // then becomes 2
                     if (n != w) *p = n;
                 }
-            } else if (s == rd.nfree + 1 && rd.blocked) {
+            } else if (s == nfree + 1 && blocked) {
                 v = 2.0f;
-                if (rd.wall && rd.dz == 0) {
-                    const int cx = x + rd.dx * s, cy = y + rd.dy * s;
+                if (wall && d < 4) {
+                    const int cx = x + dx * s, cy = y + dy * s;
                     uint32_t *p = K + s_index(R, cx, cy);
                     uint32_t w = *p, n = w | (1u << z) | (1u << (16 + z));
                     if (n != w) *p = n;
                 }
             }
-            if (obs_row) obs_row[i] = v;
+            if (obs_row) obs_row[d * L + s - 1] = v;
         }
     }
     if (obs_row) {
-        for (int i = lane; i < 7; i += G)
-            obs_row[6 * L + i] = i < 6 ? ldg(P.dist_lut + ray[i].nfree) : (float)last_action;
+        for (int i = lane; i < 7; i += G) {
+            float v = (float)last_action;
+            if (i < 6) {
+                int a = i;
+                if (i < 4) { const int h = (facing + ((0x2130 >> (4 * i)) & 3)) & 3; a = (0x1302 >> (4 * h)) & 3; }
+                v = ldg(P.dist_lut + (int)((nf6 >> (8 * a)) & 0xff));
+            }
+            obs_row[6 * L + i] = v;
+        }
     }
     if (lane == 0 && centre_new != centre_mem) K[s_index(R, x, y)] = centre_new;
     (void)lane_in_warp;

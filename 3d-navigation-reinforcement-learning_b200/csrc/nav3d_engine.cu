@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(kBlock) simple_reset_kernel(EngineParams P, co
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kBlock) simple_step_kernel(EngineParams P, StepIO io) {
+template <int G, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) simple_step_kernel(EngineParams P, StepIO io) {
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
     const long long env = gid / G;
     if (env >= P.n_envs) return;
@@ -421,8 +421,9 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
         return fail(NAV3D_ERR_INVALID, "env_kind must be NAV3D_ENV_CUBIC or NAV3D_ENV_SIMPLE");
     if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
-    // Default from the sweeps in DESIGN.md §6: 4 lanes per env at 64 registers (__launch_bounds__(128, 8)).
-    int G = cfg->lanes_per_env == 0 ? 4 : cfg->lanes_per_env;
+    // Defaults from the sweeps in DESIGN.md §6: CubicEnv 4 lanes per env at 64 registers (__launch_bounds__(128, 8));
+    // simpleEnv (6L ray cells, no window) 2 lanes per env.
+    int G = cfg->lanes_per_env == 0 ? (cfg->env_kind == NAV3D_ENV_SIMPLE ? 2 : 4) : cfg->lanes_per_env;
     if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
         return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
     int ndev = 0;
@@ -655,7 +656,8 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
         constexpr int G = decltype(g)::value;
         const unsigned grid = grid_for(e->cfg.n_envs, G);
         if (e->simple) {
-            simple_step_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
+            if (minb == 6) simple_step_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io);
+            else simple_step_kernel<G, 8><<<grid, kBlock, 0, s>>>(e->P, io);
             return NAV3D_OK;
         }
         if (e->inline_reset) {

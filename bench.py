@@ -41,6 +41,10 @@ def workload_spec(name):
     if name == "c3":
         return dict(name="c3", envs_total=65536, room_dirs=["P2_training", "P3_training"], L=10, scaling="weak",
                     desc="BASELINE configs[2]: 65536 CubicEnv envs per GPU, rooms/P2_training + P3_training (42 rooms), L=10")
+    if name == "s4":
+        return dict(name="s4", envs_total=1 << 20, room_dirs=["P1_training"], L=4, scaling="strong", simple=True,
+                    desc="2^20 simpleEnv envs (envs/simpleEnv.py) env-sharded over the GPUs, rooms/P1_training, L=4, "
+                         "uniform random actions, auto-reset")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -48,7 +52,7 @@ def load_rooms(spec):
     from nav3d.rooms import load_room_dir
     rooms = []
     for d in spec["room_dirs"]:
-        rooms += load_room_dir(ROOT / "rooms" / d, sort=True)
+        rooms += load_room_dir(ROOT / "rooms" / d, sort=True, simple=bool(spec.get("simple")))
     return rooms
 
 
@@ -167,7 +171,7 @@ def time_steps(eng, n, steps, warmup, torch, dist, world, lanes_note=None, ring=
     dev = eng.device
     g = torch.Generator(device=dev).manual_seed(1234 + seed)
     actions = torch.randint(0, 6, (act_rows, n), generator=g, device=dev, dtype=torch.int64)
-    obs = torch.empty((ring, n, 80), dtype=torch.float32, device=dev)
+    obs = torch.empty((ring, n, eng.obs_dim), dtype=torch.float32, device=dev)
     rew = torch.empty(n, dtype=torch.float32, device=dev)
     te = torch.empty(n, dtype=torch.uint8, device=dev)
     tr = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -229,7 +233,7 @@ def time_steps_graph(eng, n, steps, torch, graph_len=50, ring=4, act_rows=16):
 def time_e2e(eng, n, steps, torch, dist, world):
     dev = eng.device
     a = [torch.randint(0, 6, (n,), dtype=torch.int64).pin_memory() for _ in range(4)]
-    obs = torch.empty((n, 80), dtype=torch.float32).pin_memory()
+    obs = torch.empty((n, eng.obs_dim), dtype=torch.float32).pin_memory()
     rew = torch.empty(n, dtype=torch.float32).pin_memory()
     te = torch.empty(n, dtype=torch.uint8).pin_memory()
     tr = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -249,7 +253,7 @@ def time_e2e(eng, n, steps, torch, dist, world):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         sec = float(tmax.item())
     checksum = float(rew.sum())
-    return sec, n * 8, n * (80 * 4 + 4 + 1 + 1), checksum
+    return sec, n * 8, n * (eng.obs_dim * 4 + 4 + 1 + 1), checksum
 
 
 def time_training(torch, dist, world, rank, local_rank, n_envs=16384, n_steps=128, iters=3):
@@ -299,7 +303,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="nav3d", choices=["nav3d", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "s4"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per env (0 = engine default)")
     ap.add_argument("--envs", type=int, default=0, help="override the total env count")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads and the CPU baseline")
@@ -336,7 +340,7 @@ def main():
         n_local = spec["envs_total"]
         n_total = n_local * world
     eng = Engine(n_local, rooms, local_map_length=L, seed=2024, env_id0=rank * n_local, device=local_rank,
-                 lanes_per_env=args.lanes)
+                 lanes_per_env=args.lanes, env_kind=1 if spec.get("simple") else 0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -355,6 +359,8 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     balg = B_ALG.get(L, 334 + 64 + 64 + 12 * L + 2 + (6 * L + 1 + 7) // 8)
+    if spec.get("simple"):
+        balg = (6 * L + 7) * 4 + 14 + 64 + 2 * 6 * L + 2 + 4          # 256 B at L = 4
     launch_ms = ms_local / args.steps
     achieved = balg * n_local / (launch_ms * 1e-3) / 1e9
     traffic = None
@@ -365,7 +371,7 @@ def main():
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": f"step_call_kernel<{eng.lanes_per_env}>",
+                "traffic": traffic, "kernel": ("simple_step_kernel" if spec.get("simple") else "step_call_kernel") + f"<{eng.lanes_per_env}>",
                 "algorithmic_bytes_per_env_step": balg, "env_steps_per_launch": n_local,
                 "launch_ms": launch_ms, "peak_source": peak_src}
 
@@ -401,6 +407,41 @@ def main():
                 extra[wl]["cuda_graph"] = {"error": str(ex)}
             del e2
             torch.cuda.empty_cache()
+        # simpleEnv (envs/simpleEnv.py, the reference's older env variant): same timing method, 2^20 envs, L = 4
+        try:
+            from nav3d import _lib as nlib
+            from nav3d.rooms import load_room_dir
+            srooms = load_room_dir(ROOT / "rooms" / "P1_training", simple=True, sort=True)
+            ns = 1 << 20
+            es = Engine(ns, srooms, local_map_length=4, seed=2024, device=local_rank, lanes_per_env=args.lanes,
+                        env_kind=nlib.ENV_SIMPLE)
+            dsim = es.obs_dim
+            g = torch.Generator(device=es.device).manual_seed(7)
+            acts = torch.randint(0, 6, (16, ns), generator=g, device=es.device, dtype=torch.int64)
+            sobs = torch.empty((4, ns, dsim), dtype=torch.float32, device=es.device)
+            srew = torch.empty(ns, dtype=torch.float32, device=es.device)
+            ste = torch.empty(ns, dtype=torch.uint8, device=es.device); strn = torch.empty(ns, dtype=torch.uint8, device=es.device)
+            es.reset(sobs[0])
+            for t in range(20):
+                es.step(acts[t % 16], sobs[t % 4], srew, ste, strn)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ks = 300
+            ev0.record()
+            for t in range(ks):
+                es.step(acts[t % 16], sobs[t % 4], srew, ste, strn)
+            ev1.record()
+            torch.cuda.synchronize()
+            msim = ev0.elapsed_time(ev1)
+            extra["simple_env"] = {"workload": "2^20 simpleEnv envs (envs/simpleEnv.py), rooms/P1_training, L=4, random actions, auto-reset",
+                                   "value": ns * ks / (msim / 1e3), "unit": UNIT, "ms_per_step": msim / ks, "steps": ks,
+                                   "obs_dim": dsim, "lanes_per_env": es.lanes_per_env,
+                                   "roofline_frac": 256 * ns / (msim / ks * 1e-3) / 1e9 / peak,
+                                   "algorithmic_bytes_per_env_step": 256}
+            del es, sobs, acts
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            extra["simple_env"] = {"error": repr(ex)}
         # fused random-action rollout kernel (one launch = T steps of every env), c4 size
         try:
             s4 = workload_spec("c4")
