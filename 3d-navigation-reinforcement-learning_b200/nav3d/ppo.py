@@ -51,7 +51,7 @@ class RecurrentPPO:
                  clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  normalize_advantage: bool = True, seq_len: Optional[int] = None, seed: Optional[int] = 0,
                  verbose: int = 0, ops=None, device=None, policy: str = "MlpLstmPolicy", allow_tf32: bool = True,
-                 cuda_graph: bool = True):
+                 cuda_graph: bool = True, graph_chunk: int = 128):
         if policy != "MlpLstmPolicy":
             raise ValueError("only MlpLstmPolicy is implemented (the one the reference trains)")
         self.policy_kwargs = dict(policy_kwargs or {})
@@ -60,7 +60,7 @@ class RecurrentPPO:
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
         self.normalize_advantage = bool(normalize_advantage)
         self.seed, self.verbose = seed, int(verbose)
-        self.cuda_graph = bool(cuda_graph)
+        self.cuda_graph, self.graph_chunk = bool(cuda_graph), int(graph_chunk)
         self.num_timesteps = 0
         self.n_updates = 0
         self._iteration = 0
@@ -180,7 +180,8 @@ class RecurrentPPO:
         On a CUDA device, from the second rollout on, the whole rollout — n_steps x (policy forward, sampling kernel, env
         step kernel, bootstrap, statistics) + GAE — is ONE CUDA graph replay (env and policy inference
         fused into one launch from the host's point of view).  The first rollout runs eagerly and doubles as the warm-up
-        that graph capture needs.  Callbacks are then stepped after the replay; the policy does not change inside a
+        that graph capture needs (long rollouts are captured as several graphs of ``graph_chunk`` steps replayed back to
+        back).  Callbacks are then stepped after the replay; the policy does not change inside a
         rollout, so an evaluation triggered by them sees the same policy as it would have mid-rollout."""
         T = self.n_steps
         use_graph = self.cuda_graph and self.device.type == "cuda" and self._carry_obs
@@ -193,7 +194,8 @@ class RecurrentPPO:
                 if self.verbose:
                     print(f"CUDA-graph capture of the rollout failed ({ex!r}); continuing with eager launches")
         if use_graph:
-            self._graph.replay()
+            for graph in self._graph:
+                graph.replay()
             for _ in range(T):
                 self.num_timesteps += self.num_envs * self.world
                 if callback is not None and callback.on_step(self) is False:
@@ -221,21 +223,31 @@ class RecurrentPPO:
         return True
 
     def _capture_rollout_graph(self):
-        T = self.n_steps
+        """Capture the rollout as ceil(n_steps / graph_chunk) CUDA graphs that share one memory pool and are replayed back
+        to back (one graph of a 2 048-step rollout — ≈ 120 k nodes — takes minutes to instantiate; 128-step graphs are
+        linear in the step count).  State and episode starts flow from chunk to chunk through the static tensors."""
+        T, C = self.n_steps, max(1, min(self.n_steps, self.graph_chunk))
+        n_chunks = (T + C - 1) // C
         self._g_ep = torch.zeros(3, dtype=torch.float32, device=self.device)
-        graph = torch.cuda.CUDAGraph()
+        graphs, pool = [], None
         torch.cuda.synchronize(self.device)
-        with torch.cuda.graph(graph):
-            self._g_ep.zero_()
-            self._obs[0].copy_(self._obs[T])
-            state, starts = self._state, self._last_starts
-            for t in range(T):
-                state, starts = self._rollout_step(t, state, starts, self._g_ep, sync_free=True)
-            self._finish_rollout(state, starts)
-            for j in range(4):
-                self._state[j].copy_(state[j])
-            self._last_starts.copy_(starts)
-        self._graph = graph
+        for k in range(n_chunks):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=pool):
+                if k == 0:
+                    self._g_ep.zero_()
+                    self._obs[0].copy_(self._obs[T])
+                state, starts = self._state, self._last_starts
+                for t in range(k * C, min(T, (k + 1) * C)):
+                    state, starts = self._rollout_step(t, state, starts, self._g_ep, sync_free=True)
+                if k == n_chunks - 1:
+                    self._finish_rollout(state, starts)
+                for j in range(4):
+                    self._state[j].copy_(state[j])
+                self._last_starts.copy_(starts)
+            pool = graph.pool()
+            graphs.append(graph)
+        self._graph = graphs
 
     # ---- update ------------------------------------------------------------------------------------------------
     def _chunk_view(self, x: torch.Tensor) -> torch.Tensor:
