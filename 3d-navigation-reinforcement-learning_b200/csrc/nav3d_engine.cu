@@ -368,10 +368,21 @@ struct nav3d_engine {
 
 namespace {
 
-int set_device(const nav3d_engine *e) {
-    CUDA_TRY(cudaSetDevice(e->cfg.device));
-    return NAV3D_OK;
-}
+// Makes the engine's device current for the duration of one ABI call and puts the caller's device back afterwards: the
+// caller (torch) tracks the current device itself and must not find it changed behind its back.
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) : want(device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != want) err = cudaSetDevice(want);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+#define NAV3D_DEVICE(e)                                                                                            \
+    DeviceGuard _dev_guard((e)->cfg.device);                                                                       \
+    if (_dev_guard.err != cudaSuccess)                                                                             \
+    return fail(NAV3D_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_dev_guard.err))
 
 void free_rooms(nav3d_engine *e) {
     cudaFree(e->d_rooms); cudaFree(e->d_occz); cudaFree(e->d_occ64); cudaFree(e->d_free); cudaFree(e->d_know);
@@ -492,7 +503,7 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
 
 void nav3d_destroy(nav3d_engine *e) {
     if (!e) return;
-    cudaSetDevice(e->cfg.device);
+    DeviceGuard guard(e->cfg.device);
     free_rooms(e);
     cudaFree(e->d_states); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
     cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_pend_count); cudaFree(e->d_pend_list); cudaFree(e->d_dist_lut);
@@ -503,7 +514,7 @@ void nav3d_destroy(nav3d_engine *e) {
 int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *rooms) {
     if (!e || !rooms) return fail(NAV3D_ERR_INVALID, "engine/rooms is NULL");
     if (n_rooms <= 0 || n_rooms > 65535) return fail(NAV3D_ERR_UNSUPPORTED, "n_rooms must be in 1..65535");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     std::vector<RoomDev> hr((size_t)n_rooms);
     std::vector<uint32_t> dense_off((size_t)n_rooms);
     std::vector<int32_t> wall((size_t)n_rooms);
@@ -623,7 +634,7 @@ int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_
     if (n < 0 || (!env_ids && n > e->cfg.n_envs)) return fail(NAV3D_ERR_INVALID, "n out of range");
     if (n == 0) return NAV3D_OK;
     if (obs && !e->simple && ((uintptr_t)obs & 15u)) return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
@@ -644,7 +655,7 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
         return fail(NAV3D_ERR_INVALID, "actions, obs, reward, terminated and truncated are required");
     if (!e->simple && (((uintptr_t)obs & 15u) || (terminal_obs && ((uintptr_t)terminal_obs & 15u))))
         return fail(NAV3D_ERR_INVALID, "obs / terminal_obs must be 16-byte aligned");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     StepIO io;
     io.actions = reinterpret_cast<const long long *>(actions);
     io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = terminated; io.truncated = truncated;
@@ -696,7 +707,7 @@ int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *
                     uint8_t *truncated) {
     if (int rc = check_ready(e)) return rc;
     if (!actions || !obs || !reward || !terminated || !truncated) return fail(NAV3D_ERR_INVALID, "NULL host buffer");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     const size_t N = (size_t)e->cfg.n_envs;
     const size_t obs_dim = (size_t)e->P.obs_dim;
     if (!e->d_obs) CUDA_TRY(cudaMalloc(&e->d_obs, N * obs_dim * sizeof(float)));
@@ -723,7 +734,7 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
     if (!obs && !obs_last) return fail(NAV3D_ERR_INVALID, "one of obs / obs_last is required");
     if ((obs && ((uintptr_t)obs & 15u)) || (obs_last && ((uintptr_t)obs_last & 15u)))
         return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
@@ -740,7 +751,7 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
 int nav3d_get_state(nav3d_engine *e, int32_t *state, void *stream) {
     if (int rc = check_ready(e)) return rc;
     if (!state) return fail(NAV3D_ERR_INVALID, "state is NULL");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     get_state_kernel<<<(e->cfg.n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->P, state);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -750,7 +761,7 @@ int nav3d_get_state(nav3d_engine *e, int32_t *state, void *stream) {
 int nav3d_get_grid(nav3d_engine *e, int32_t env, int16_t *grid, void *stream) {
     if (int rc = check_ready(e)) return rc;
     if (!grid || env < 0 || env >= e->cfg.n_envs) return fail(NAV3D_ERR_INVALID, "bad env index / NULL grid");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     if (e->simple) simple_get_grid_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(e->P, env, grid);
     else get_grid_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(e->P, env, grid);
     e->launches++;
@@ -766,7 +777,7 @@ size_t nav3d_snapshot_bytes(const nav3d_engine *e) {
 int nav3d_snapshot(nav3d_engine *e, void *host_buf, size_t bytes) {
     if (int rc = check_ready(e)) return rc;
     if (!host_buf || bytes != nav3d_snapshot_bytes(e)) return fail(NAV3D_ERR_INVALID, "snapshot buffer size mismatch");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     CUDA_TRY(cudaDeviceSynchronize());
     const size_t sb = (size_t)e->cfg.n_envs * sizeof(EnvState);
     CUDA_TRY(cudaMemcpy(host_buf, e->d_states, sb, cudaMemcpyDeviceToHost));
@@ -777,7 +788,7 @@ int nav3d_snapshot(nav3d_engine *e, void *host_buf, size_t bytes) {
 int nav3d_restore(nav3d_engine *e, const void *host_buf, size_t bytes) {
     if (int rc = check_ready(e)) return rc;
     if (!host_buf || bytes != nav3d_snapshot_bytes(e)) return fail(NAV3D_ERR_INVALID, "snapshot buffer size mismatch");
-    if (int rc = set_device(e)) return rc;
+    NAV3D_DEVICE(e);
     CUDA_TRY(cudaDeviceSynchronize());
     const size_t sb = (size_t)e->cfg.n_envs * sizeof(EnvState);
     CUDA_TRY(cudaMemcpy(e->d_states, host_buf, sb, cudaMemcpyHostToDevice));
