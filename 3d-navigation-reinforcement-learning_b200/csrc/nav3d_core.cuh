@@ -539,8 +539,10 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
     const bool bumped = !moved;
 
     // Issue every load of the step now: first window batch, the counter of the final cell, the three occupancy words.
+    // (A caller that wants no observation at all — the inner steps of a fused rollout — skips the window entirely.)
+    const bool any_obs = io.obs != nullptr || io.terminal_obs != nullptr;
     WinBatch<G> wb;
-    window_load<G>(P, R, envk, lane, x, y, z, 0, wb);
+    if (any_obs) window_load<G>(P, R, envk, lane, x, y, z, 0, wb);
     const uint32_t cidx = c_index(R, x, y, z);
     const int c_old = C[cidx];
     const Rays r = cast_rays(P, R, x, y, z);
@@ -558,7 +560,7 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
     const bool will_reset = P.auto_reset && (done || truncated);
 
     // get_obs (:122)
-    float *orow = io.obs + row * kObsDim;
+    float *orow = io.obs ? io.obs + row * kObsDim : nullptr;
     if (will_reset) orow = io.terminal_obs ? io.terminal_obs + row * kObsDim : nullptr;
     if (orow != nullptr) {
         ObsScalars sc;
@@ -623,7 +625,7 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
         if (will_reset) {
             // every lane's reads of the old knowledge are done before any lane clears it
             group_sync<G>(lane_in_warp);
-            reset_env_philox<G>(P, env, lane, lane_in_warp, st.episode, lut, io.obs + row * kObsDim);
+            reset_env_philox<G>(P, env, lane, lane_in_warp, st.episode, lut, io.obs ? io.obs + row * kObsDim : nullptr);
         }
         return false;
     }

@@ -224,11 +224,15 @@ __global__ void __launch_bounds__(kBlock) reset_pending_kernel(EngineParams P, P
     }
 }
 
+// T fused steps per env with on-device Philox actions.  An env's record and the knowledge lines it
+// touches stay in L1/L2 for the whole rollout, so DRAM sees the outputs the caller asked for plus one pass over the touched
+// lines.  When only the last observation is requested the intermediate observations are never formed.  The reset is an
+// out-of-line call (as in step_call_kernel) so that the loop body keeps the step's 64 registers.
 template <int G>
-__global__ void __launch_bounds__(kBlock) rollout_kernel(EngineParams P, int T, uint32_t t0, float *obs, float *obs_last,
-                                                         float *reward, uint8_t *done, uint8_t *actions_out,
-                                                         float *reward_scratch, uint8_t *term_scratch,
-                                                         uint8_t *trunc_scratch) {
+__global__ void __launch_bounds__(kBlock, 6) rollout_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0,
+                                                            float *obs, float *obs_last, float *reward, uint8_t *done,
+                                                            uint8_t *actions_out, float *reward_scratch,
+                                                            uint8_t *term_scratch, uint8_t *trunc_scratch) {
     __shared__ float lut[24];
     fill_lut(lut);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -242,12 +246,17 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(EngineParams P, int T, 
         const int action = (int)mulhi_range(u0, 6u);
         StepIO io;
         io.actions = nullptr;
-        io.obs = obs ? obs + (long long)t * N * kObsDim : obs_last;
+        // obs == NULL: only the last step's observation is kept; the earlier steps form none (and skip the window gather)
+        io.obs = obs ? obs + (long long)t * N * kObsDim : (t == T - 1 ? obs_last : nullptr);
         io.reward = reward ? reward + (long long)t * N : reward_scratch;
         io.reward64 = nullptr;
         io.terminated = term_scratch; io.truncated = trunc_scratch;
         io.terminal_obs = nullptr; io.episodes = nullptr;
-        step_env<G, true>(P, io, (int)env, lane, liw, action, lut, env);
+        if (step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env)) {
+            const uint32_t episode = P.states[env].episode;
+            group_sync<G>(liw);
+            reset_out_of_line<G>(P, (int)env, lane, liw, episode, lut, io.obs ? io.obs + env * kObsDim : nullptr);
+        }
         if (lane == 0) {
             if (done) done[(long long)t * N + env] = term_scratch[env] | trunc_scratch[env];
             if (actions_out) actions_out[(long long)t * N + env] = (uint8_t)action;
@@ -729,6 +738,7 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
                          uint8_t *done, uint8_t *actions_out, void *stream) {
     if (int rc = check_ready(e)) return rc;
     if (T < 0) return fail(NAV3D_ERR_INVALID, "T must be >= 0");
+
     if (e->simple) return fail(NAV3D_ERR_UNSUPPORTED, "nav3d_rollout_random is implemented for NAV3D_ENV_CUBIC only");
     if (T == 0) return NAV3D_OK;
     if (!obs && !obs_last) return fail(NAV3D_ERR_INVALID, "one of obs / obs_last is required");

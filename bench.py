@@ -446,7 +446,7 @@ def main():
         try:
             s4 = workload_spec("c4")
             e4 = Engine(s4["envs_total"], load_rooms(s4), local_map_length=10, seed=2024, device=local_rank,
-                        lanes_per_env=args.lanes)
+                        lanes_per_env=args.lanes or 2)       # 2 lanes per env suit the fused loop (tools/rollout_bench.py)
             n4, T = s4["envs_total"], 32
             obs = e4.reset()
             rew = torch.empty((T, n4), dtype=torch.float32, device=e4.device)
@@ -462,8 +462,9 @@ def main():
             torch.cuda.synchronize()
             mr = ev0.elapsed_time(ev1)
             extra["fused_rollout_c4"] = {"value": n4 * T * reps / (mr / 1e3), "unit": UNIT, "T": T,
-                                         "note": "nav3d_rollout_random: on-device Philox actions, last observation + "
-                                                 "per-step reward/done kept"}
+                                         "lanes_per_env": e4.lanes_per_env,
+                                         "note": "nav3d_rollout_random: T steps per launch, on-device Philox actions, last "
+                                                 "observation + per-step reward/done kept (the inner steps form no observation)"}
             del e4
             torch.cuda.empty_cache()
         except Exception as ex:  # noqa: BLE001
