@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (read here, no GPU): key counters per kernel. usage: tools_ncu_summary.py file.ncu-rep [n_envs]"""
+"""Summarise an .ncu-rep (read here, no GPU): key counters per kernel. usage: tools/ncu_summary.py file.ncu-rep [n_envs]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; n = float(sys.argv[2]) if len(sys.argv) > 2 else 1048576.0
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_sweep.sh "<lanes list>" "<minb list>" [extra bench args]
+# usage: tools/sweep.sh "<lanes list>" "<minb list>" [extra bench args]
 for l in $1; do for m in $2; do
   NAV3D_MINB=$m python bench.py --steps 200 --warmup 10 --no-extras --lanes $l $3 > gpurun_out/sw_${l}_${m}.log 2>&1
   python - <<PY
