@@ -51,7 +51,7 @@ class RecurrentPPO:
                  clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  normalize_advantage: bool = True, seq_len: Optional[int] = None, seed: Optional[int] = 0,
                  verbose: int = 0, ops=None, device=None, policy: str = "MlpLstmPolicy", allow_tf32: bool = True,
-                 cuda_graph: bool = True, graph_chunk: int = 128):
+                 cuda_graph: bool = True, graph_chunk: int = 128, graph_update_max: int = 8192):
         if policy != "MlpLstmPolicy":
             raise ValueError("only MlpLstmPolicy is implemented (the one the reference trains)")
         self.policy_kwargs = dict(policy_kwargs or {})
@@ -60,7 +60,7 @@ class RecurrentPPO:
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
         self.normalize_advantage = bool(normalize_advantage)
         self.seed, self.verbose = seed, int(verbose)
-        self.cuda_graph, self.graph_chunk = bool(cuda_graph), int(graph_chunk)
+        self.cuda_graph, self.graph_chunk, self.graph_update_max = bool(cuda_graph), int(graph_chunk), int(graph_update_max)
         self.num_timesteps = 0
         self.n_updates = 0
         self._iteration = 0
@@ -87,7 +87,9 @@ class RecurrentPPO:
         if self._dist is not None:                                   # identical replicas: rank 0's initialisation wins
             for p in self.policy.parameters():
                 self._dist.broadcast(p.data, src=0)
-        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.learning_rate, eps=1e-5)
+        # capturable: the step counter lives on the device, so an optimizer step can be part of a CUDA graph
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.learning_rate, eps=1e-5,
+                                          capturable=self.device.type == "cuda")
         self._ops = ops
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(seed or 0) + 7919)
@@ -135,6 +137,8 @@ class RecurrentPPO:
         self._obs[0].copy_(env.reset())
         self._carry_obs = False           # True once obs[T] of a finished rollout has to become obs[0] of the next
         self._graph = None                # CUDA graph of one whole rollout (captured at the second rollout)
+        self._upd = self._upd_graph = None   # CUDA graph of one minibatch update (small minibatches only)
+        self._upd_warm = 0
         # Philox policy-stream position: a device counter (so a captured rollout draws fresh numbers on replay)
         self._step_base = torch.zeros(1, dtype=torch.int32, device=dev) if dev.type == "cuda" else None
 
@@ -258,59 +262,111 @@ class RecurrentPPO:
         rest = x.shape[2:]
         return x.reshape(K, S, N, *rest).transpose(0, 1).reshape(S, K * N, *rest)
 
+    def _minibatch(self, data: dict, idx: torch.Tensor, cuts, acc: torch.Tensor) -> None:
+        """One PPO minibatch update on the sequences ``idx`` (columns of the chunk-view tensors in ``data``): forward over
+        the sequences, clipped surrogate + value + entropy loss, backward into the flat gradient buffer, (all-reduce,)
+        norm clip, Adam step; running sums of the statistics go to ``acc``.  Sync-free, so it can be captured."""
+        pol = self.policy
+        mb_obs = data["obs"].index_select(1, idx)
+        mb_state = tuple(data["state0"][j].index_select(1, idx).contiguous() for j in range(4))
+        mb_starts = data["starts"].index_select(1, idx)
+        logits, values, _ = pol.forward_sequence(mb_obs, mb_state, mb_starts, cuts)
+        logp_all = F.log_softmax(logits, dim=-1)
+        mb_actions = data["actions"].index_select(1, idx)
+        logp = logp_all.gather(-1, mb_actions.unsqueeze(-1)).squeeze(-1)
+        entropy = -(logp_all.exp() * logp_all).sum(-1)
+        adv = data["adv"].index_select(1, idx)
+        if self.normalize_advantage and adv.numel() > 1:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        old_logp = data["old_logp"].index_select(1, idx)
+        ratio = torch.exp(logp - old_logp)
+        pl1 = adv * ratio
+        pl2 = adv * torch.clamp(ratio, 1.0 - self.clip_range, 1.0 + self.clip_range)
+        policy_loss = -torch.min(pl1, pl2).mean()
+        value_loss = F.mse_loss(data["ret"].index_select(1, idx), values)
+        entropy_loss = -entropy.mean()
+        loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
+        self._flat_grad.zero_()
+        loss.backward()
+        if self._dist is not None:
+            self._dist.all_reduce(self._flat_grad)
+            self._flat_grad.div_(self.world)
+        gnorm = self._flat_grad.norm()
+        self._flat_grad.mul_(torch.clamp(self.max_grad_norm / (gnorm + 1e-6), max=1.0))
+        self.optimizer.step()
+        with torch.no_grad():
+            log_ratio = logp - old_logp
+            acc += torch.stack([policy_loss, value_loss, entropy_loss, ((ratio - 1.0) - log_ratio).mean(),
+                                ((ratio - 1.0).abs() > self.clip_range).float().mean(), loss]).detach()
+
+    def _update_graph_wanted(self, n_seq: int, b_seq: int) -> bool:
+        """Small minibatches are bound by ≈ 700 kernel launches each (the reference's 64-transition minibatches take
+        4.9 ms eagerly for well under 1 ms of device work): replay them as one CUDA graph.  Large minibatches are device-
+        bound and keep the eager path, where the critic branch overlaps the actor's on a second stream."""
+        return (self.cuda_graph and self.device.type == "cuda" and self._dist is None and n_seq % b_seq == 0
+                and b_seq * self.seq_len <= self.graph_update_max and self.policy.n_lstm_layers == 1
+                and self.policy.fused_lstm)
+
     def train(self) -> Dict[str, float]:
         pol, S, T, N = self.policy, self.seq_len, self.n_steps, self.num_envs
         K = T // S
         n_seq = K * N
         b_seq = max(1, min(n_seq, self.batch_size // S))
-        obs = self._chunk_view(self._obs[:T])
-        actions, old_logp = self._chunk_view(self._actions), self._chunk_view(self._logp)
-        adv_all, ret_all = self._chunk_view(self._adv), self._chunk_view(self._ret)
-        starts = self._chunk_view(self._starts)
-        state0 = self._chunk_states.permute(1, 2, 0, 3, 4).reshape(4, pol.n_lstm_layers, n_seq, pol.lstm_hidden_size)
-        # timesteps (relative to a chunk) at which any sequence has an episode start: the only places where the LSTM
-        # state must be masked, so cuDNN runs whole stretches in between.  One small device->host read per rollout.
-        cut_flags = starts.any(dim=1).cpu().numpy()
-        cuts = [0] + [int(t) for t in np.nonzero(cut_flags)[0] if t > 0]
+        fresh = dict(obs=self._chunk_view(self._obs[:T]), actions=self._chunk_view(self._actions),
+                     old_logp=self._chunk_view(self._logp), adv=self._chunk_view(self._adv), ret=self._chunk_view(self._ret),
+                     starts=self._chunk_view(self._starts),
+                     state0=self._chunk_states.permute(1, 2, 0, 3, 4).reshape(4, pol.n_lstm_layers, n_seq, pol.lstm_hidden_size))
+        use_graph = self._update_graph_wanted(n_seq, b_seq)
+        if use_graph:
+            # the graph reads its operands from fixed addresses: keep the chunk views in persistent buffers
+            if self._upd is None:
+                self._upd = {k: torch.empty_like(v) for k, v in fresh.items()}
+                self._upd_idx = torch.zeros(b_seq, dtype=torch.int64, device=self.device)
+                self._upd_acc = torch.zeros(6, dtype=torch.float32, device=self.device)
+                self._upd_stream = torch.cuda.Stream(device=self.device)
+            for k, v in fresh.items():
+                self._upd[k].copy_(v)
+            data, acc, cuts = self._upd, self._upd_acc, (0,)
+            acc.zero_()
+            # everything of a captured minibatch lives on ONE stream (also the warm-up runs, so that autograd's gradient
+            # accumulators are bound to the capture stream and not to the policy's side stream)
+            two_streams, pol.two_streams = pol.two_streams, False
+        else:
+            data = fresh
+            acc = torch.zeros(6, dtype=torch.float32, device=self.device)
+            # timesteps (relative to a chunk) at which any sequence has an episode start: the only places where the LSTM
+            # state must be masked when cuDNN runs the stretches in between.  One small device->host read per rollout.
+            cut_flags = data["starts"].any(dim=1).cpu().numpy()
+            cuts = [0] + [int(t) for t in np.nonzero(cut_flags)[0] if t > 0]
         stats = dict(policy_loss=0.0, value_loss=0.0, entropy_loss=0.0, approx_kl=0.0, clip_fraction=0.0, loss=0.0)
-        acc = torch.zeros(6, dtype=torch.float32, device=self.device)
         n_mb = 0
         for _ in range(self.n_epochs):
             perm = torch.randperm(n_seq, device=self.device, generator=self._gen)
             for i0 in range(0, n_seq, b_seq):
                 idx = perm[i0:i0 + b_seq]
-                mb_obs = obs.index_select(1, idx)
-                mb_state = tuple(state0[j].index_select(1, idx).contiguous() for j in range(4))
-                mb_starts = starts.index_select(1, idx)
-                logits, values, _ = pol.forward_sequence(mb_obs, mb_state, mb_starts, cuts)
-                logp_all = F.log_softmax(logits, dim=-1)
-                mb_actions = actions.index_select(1, idx)
-                logp = logp_all.gather(-1, mb_actions.unsqueeze(-1)).squeeze(-1)
-                entropy = -(logp_all.exp() * logp_all).sum(-1)
-                adv = adv_all.index_select(1, idx)
-                if self.normalize_advantage and adv.numel() > 1:
-                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                ratio = torch.exp(logp - old_logp.index_select(1, idx))
-                pl1 = adv * ratio
-                pl2 = adv * torch.clamp(ratio, 1.0 - self.clip_range, 1.0 + self.clip_range)
-                policy_loss = -torch.min(pl1, pl2).mean()
-                value_loss = F.mse_loss(ret_all.index_select(1, idx), values)
-                entropy_loss = -entropy.mean()
-                loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
-                self._flat_grad.zero_()
-                loss.backward()
-                if self._dist is not None:
-                    self._dist.all_reduce(self._flat_grad)
-                    self._flat_grad.div_(self.world)
-                gnorm = self._flat_grad.norm()
-                self._flat_grad.mul_(torch.clamp(self.max_grad_norm / (gnorm + 1e-6), max=1.0))
-                self.optimizer.step()
-                with torch.no_grad():
-                    log_ratio = logp - old_logp.index_select(1, idx)
-                    acc += torch.stack([policy_loss, value_loss, entropy_loss, ((ratio - 1.0) - log_ratio).mean(),
-                                        ((ratio - 1.0).abs() > self.clip_range).float().mean(), loss]).detach()
+                if not use_graph:
+                    self._minibatch(data, idx, cuts, acc)
+                else:
+                    cur = torch.cuda.current_stream(self.device)
+                    self._upd_idx.copy_(idx)
+                    self._upd_stream.wait_stream(cur)
+                    if self._upd_graph is None and self._upd_warm < 2:
+                        with torch.cuda.stream(self._upd_stream):          # eager warm-up on the capture stream
+                            self._minibatch(data, self._upd_idx, cuts, acc)
+                        self._upd_warm += 1
+                    else:
+                        if self._upd_graph is None:
+                            graph = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(graph, stream=self._upd_stream, capture_error_mode="thread_local"):
+                                self._minibatch(data, self._upd_idx, cuts, acc)
+                            self._upd_graph = graph
+                        with torch.cuda.stream(self._upd_stream):
+                            self._upd_graph.replay()
+                    cur.wait_stream(self._upd_stream)
                 n_mb += 1
             self.n_updates += 1
+        if use_graph:
+            pol.two_streams = two_streams
         vals = (acc / max(1, n_mb)).cpu().tolist()
         for k, v in zip(("policy_loss", "value_loss", "entropy_loss", "approx_kl", "clip_fraction", "loss"), vals):
             stats[k] = float(v)

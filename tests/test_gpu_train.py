@@ -232,3 +232,45 @@ def test_cuda_graph_rollout_equals_eager_rollout():
     # training between graph replays keeps working (the graph reads the parameters in place)
     b.train()
     assert b.collect_rollouts()
+
+
+def test_cuda_graph_update_equals_eager_update():
+    """Small minibatches (launch-bound) are replayed as ONE CUDA graph per minibatch (forward, backward, clip, Adam); after
+    the same rollouts and the same shuffles the parameters must agree with the eager update."""
+    from nav3d import BatchedCubicEnv
+    from nav3d.ppo import RecurrentPPO
+    from nav3d.rooms import load_room_file
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt")]
+    try:
+        models = []
+        for graph in (False, True):
+            env = BatchedCubicEnv(rooms=rooms, num_envs=8, local_map_length=10, seed=5)
+            m = RecurrentPPO(env, policy_kwargs=dict(net_arch=dict(pi=[64, 64], vf=[64, 64]), lstm_hidden_size=64), n_steps=64,
+                             batch_size=32, n_epochs=2, ent_coef=0.01, seed=3, cuda_graph=graph, allow_tf32=False)
+            models.append(m)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        a, b = models
+        # two iterations: the first holds the eager warm-up minibatches, the capture and replays, the second replays only.
+        # (Adam turns rounding-level gradient differences into lr-sized steps, so longer runs drift apart legitimately.)
+        for it in range(2):
+            for m in models:
+                m.collect_rollouts()
+            assert torch.equal(a._actions, b._actions), it            # same policy so far -> same rollout
+            sa, sb = a.train(), b.train()
+            assert sa["minibatches"] == sb["minibatches"] == 2 * (64 * 8 // 32)
+            pa = torch.cat([p.detach().flatten() for p in a.policy.parameters()])
+            pb = torch.cat([p.detach().flatten() for p in b.policy.parameters()])
+            rel = float((pa - pb).norm() / pa.norm())
+            assert rel < 5e-4, (it, rel)
+            for k in ("policy_loss", "value_loss", "entropy_loss", "approx_kl"):
+                assert abs(sa[k] - sb[k]) <= 1e-3 * (1.0 + abs(sa[k])), (k, sa[k], sb[k])
+        assert b._upd_graph is not None and a._upd_graph is None
+        # the optimizer state of a graph-trained model survives a checkpoint round trip
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            path = b.save(d + "/m")
+            c = RecurrentPPO.load(path, env=BatchedCubicEnv(rooms=rooms, num_envs=8, local_map_length=10, seed=5))
+            c.collect_rollouts(); c.train()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
