@@ -9,7 +9,8 @@ edge (real out-of-bounds paths in ``maze_7x7_*``, ``maze_8x8_*``, ``maze_dead1_1
 be reached from each other make the 84 % finish line (``CubicEnv.py:12``, ``:212``) unreachable.
 
     python -m nav3d.room_tools validate rooms/P3_training
-    python -m nav3d.room_tools generate --kind maze --size 21,21,9 --seed 3 -o my_maze.txt"""
+    python -m nav3d.room_tools generate --kind maze --size 21,21,9 --seed 3 -o my_maze.txt
+    python -m nav3d.room_tools compose --objects rooms/objects --size 32,32,12 --count 6 -o my_flat.txt"""
 from __future__ import annotations
 
 import argparse
@@ -224,6 +225,76 @@ def generate_room(kind: str, size: Tuple[int, int, int], seed: int = 0, density:
     raise ValueError(f"unknown room kind {kind!r} (empty, maze, furnished)")
 
 
+# ---- furniture stamps (rooms/objects) ---------------------------------------------------------------------------------
+def parse_stamp_text(text: str) -> np.ndarray:
+    """A furniture stamp of ``rooms/objects`` (``Layer=k`` headers, each followed by rows of 0/2 values; no ``Size=``; the
+    reference ships them as copy/paste aids that no code loads).  Returns ``stamp[x, y, k]`` with 1 where the file has a 2;
+    text column -> x and text row -> y as in room files; layers the file does not mention are empty."""
+    layers: Dict[int, List[List[int]]] = {}
+    cur = None
+    for raw in text.splitlines():
+        line = raw.strip()
+        if not line:
+            continue
+        if line.startswith("Layer"):
+            cur = int(line.split("=")[1])
+            layers[cur] = []
+        elif cur is not None:
+            layers[cur].append([int(v) for v in line.split()])
+    if not layers:
+        raise ValueError("stamp has no Layer= block")
+    w = max(len(r) for rows in layers.values() for r in rows)
+    d = max(len(rows) for rows in layers.values())
+    h = max(layers) + 1
+    out = np.zeros((w, d, h), dtype=np.int8)
+    for k, rows in layers.items():
+        if k < 0:
+            raise ValueError("negative stamp layer")
+        for y, row in enumerate(rows):
+            for x, v in enumerate(row):
+                out[x, y, k] = 1 if v == 2 else 0
+    return out
+
+
+def stamp_object(grid: np.ndarray, stamp: np.ndarray, x0: int, y0: int, rotate: int = 0, *, allow_overlap: bool = True) -> bool:
+    """OR ``stamp`` (rotated ``rotate`` quarter turns about z) into the CubicEnv room ``grid`` with its (0, 0) corner at
+    column (x0, y0); stamp layer k lands on room layer z = k (stamps start at ``Layer=1``, the first layer above the
+    floor).  Returns False and leaves the room untouched when the stamp does not fit inside the shell (or, with
+    ``allow_overlap=False``, would touch an existing wall cell of the interior)."""
+    st = np.rot90(stamp, k=rotate % 4, axes=(0, 1))
+    w, d, h = st.shape
+    W, D, H = grid.shape
+    if x0 < 1 or y0 < 1 or x0 + w > W - 1 or y0 + d > D - 1 or h > H - 1:
+        return False
+    region = grid[x0:x0 + w, y0:y0 + d, 0:h]
+    if not allow_overlap and bool(((region == CUBIC_WALL) & (st == 1))[:, :, 1:].any()):
+        return False
+    region[st == 1] = CUBIC_WALL
+    return True
+
+
+def load_stamps(objects_dir) -> Dict[str, np.ndarray]:
+    return {p.name: parse_stamp_text(p.read_text()) for p in sorted(Path(objects_dir).iterdir()) if p.is_file()}
+
+
+def furnish_room(size: Tuple[int, int, int], stamps: Dict[str, np.ndarray], n_objects: int, seed: int = 0) -> np.ndarray:
+    """A hollow box with ``n_objects`` randomly chosen, randomly rotated stamps placed without overlap (best effort)."""
+    rng = np.random.default_rng(seed)
+    g = _shell(*size)
+    names = sorted(stamps)
+    placed = tries = 0
+    while placed < n_objects and tries < 200 * max(1, n_objects):
+        tries += 1
+        st = stamps[names[int(rng.integers(len(names)))]]
+        rot = int(rng.integers(4))
+        w, d = (st.shape[0], st.shape[1]) if rot % 2 == 0 else (st.shape[1], st.shape[0])
+        if size[0] - 2 < w or size[1] - 2 < d:
+            continue
+        x0, y0 = int(rng.integers(1, size[0] - 1 - w + 1)), int(rng.integers(1, size[1] - 1 - d + 1))
+        placed += stamp_object(g, st, x0, y0, rot, allow_overlap=False)
+    return g
+
+
 # ---- CLI -------------------------------------------------------------------------------------------------------------
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="python -m nav3d.room_tools", description=__doc__,
@@ -240,6 +311,12 @@ def main(argv=None) -> int:
     gsub.add_argument("--seed", type=int, default=0)
     gsub.add_argument("--density", type=float, default=0.15)
     gsub.add_argument("-o", "--output", required=True)
+    c = sub.add_parser("compose", help="hollow box furnished with stamps from a rooms/objects directory")
+    c.add_argument("--objects", required=True)
+    c.add_argument("--size", default="32,32,12")
+    c.add_argument("--count", type=int, default=6)
+    c.add_argument("--seed", type=int, default=0)
+    c.add_argument("-o", "--output", required=True)
     args = ap.parse_args(argv)
     if args.cmd == "validate":
         p = Path(args.path)
@@ -256,6 +333,9 @@ def main(argv=None) -> int:
         Path(args.output).write_text(normalise_room_text(Path(args.path).read_text()))
         return 0
     size = tuple(int(x) for x in args.size.split(","))
+    if args.cmd == "compose":
+        Path(args.output).write_text(room_to_text(furnish_room(size, load_stamps(args.objects), args.count, args.seed)))
+        return 0
     Path(args.output).write_text(room_to_text(generate_room(args.kind, size, args.seed, args.density)))
     return 0
 

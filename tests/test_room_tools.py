@@ -6,11 +6,11 @@ import numpy as np
 import pytest
 
 from conftest import ROOMS
-from nav3d.room_tools import (generate_room, main, normalise_room_text, room_to_text, validate_room_file,
-                              validate_room_text)
+from nav3d.room_tools import (furnish_room, generate_room, load_stamps, main, normalise_room_text, parse_stamp_text,
+                              room_to_text, stamp_object, validate_room_file, validate_room_text)
 from nav3d.rooms import parse_room_text
 
-ALL_ROOMS = sorted(ROOMS.glob("*/*.txt"))
+ALL_ROOMS = sorted(p for p in ROOMS.glob("*/*.txt") if p.parent.name != "objects")
 
 
 def test_writer_inverts_parser_on_every_shipped_room():
@@ -91,3 +91,26 @@ def test_cli_validate_and_generate(tmp_path, capsys):
     norm = tmp_path / "k2.txt"
     assert main(["normalise", str(ROOMS / "P3_training" / "kitchen2.txt"), "-o", str(norm)]) == 0
     assert validate_room_file(norm).findings.get("negative_layer_index") is None
+
+
+def test_furniture_stamps_compose_into_rooms(tmp_path):
+    """rooms/objects: the reference's furniture stamps (Layer=k blocks, no Size=) parse, rotate and stamp into a room."""
+    stamps = load_stamps(ROOMS / "objects")
+    assert len(stamps) == 8 and all(s.any() and s[:, :, 0].sum() == 0 for s in stamps.values())     # stamps start at Layer=1
+    closet = stamps["closet.txt"]
+    assert closet.shape[:2] == (5, 9) and closet[:, :, 1:].all()                                      # a solid 5 x 9 block
+    tiny = parse_stamp_text("Layer=1\n2 0\n2 2\nLayer=2\n2 0\n0 0\n")
+    assert tiny.shape == (2, 2, 3) and tiny[:, :, 1].tolist() == [[1, 1], [0, 1]] and tiny[0, 0, 2] == 1
+    room = generate_room("empty", (12, 10, 6))
+    assert stamp_object(room, tiny, 3, 4)
+    assert room[3, 4, 1] == -2 and room[3, 5, 1] == -2 and room[4, 5, 1] == -2 and room[4, 4, 1] == 0 and room[3, 4, 2] == -2
+    assert not stamp_object(room, tiny, 10, 4) and not stamp_object(room, tiny, 3, 4, allow_overlap=False)   # shell / overlap
+    quarter = generate_room("empty", (12, 10, 6))
+    assert stamp_object(quarter, tiny, 3, 4, rotate=1) and not np.array_equal(quarter, room)
+    flat = furnish_room((40, 32, 12), stamps, 6, seed=4)
+    assert np.array_equal(flat, furnish_room((40, 32, 12), stamps, 6, seed=4))
+    rep = validate_room_text(room_to_text(flat))
+    assert not rep.errors and "open_shell_cells" not in rep.findings and rep.n_wall > generate_room("empty", (40, 32, 12)).astype(bool).sum()
+    out = tmp_path / "flat.txt"
+    assert main(["compose", "--objects", str(ROOMS / "objects"), "--size", "32,32,12", "--count", "5", "-o", str(out)]) == 0
+    assert validate_room_file(out).n_free_interior > 0
