@@ -79,6 +79,7 @@ struct StepIO {                    // per-launch output pointers (any may be nul
     uint8_t *terminated, *truncated;
     float *terminal_obs;
     void *episodes;                // nav3d_episode*
+    int env0, env_n;               // the launch covers envs [env0, env0 + env_n); outputs are indexed by the env itself
 };
 
 // ---------------------------------------------------------------------------------------------------------------

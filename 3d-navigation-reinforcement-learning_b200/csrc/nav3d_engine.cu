@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(kBlock, MINB) step_kernel(EngineParams P, Step
     __shared__ float lut[24];
     fill_lut(lut);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const long long env = gid / G;
-    if (env >= P.n_envs) return;
+    if (gid / G >= io.env_n) return;
+    const long long env = io.env0 + gid / G;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
     const int action = (int)io.actions[env];
     const bool need_reset = step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env) && lane == 0;
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_co
     __shared__ float lut[24];
     fill_lut(lut);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const long long env = gid / G;
-    if (env >= P.n_envs) return;
+    if (gid / G >= io.env_n) return;
+    const long long env = io.env0 + gid / G;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
     const int action = (int)io.actions[env];
     if (step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env)) {
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(kBlock) step_inline_kernel(EngineParams P, Ste
     __shared__ float lut[24];
     fill_lut(lut);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const long long env = gid / G;
-    if (env >= P.n_envs) return;
+    if (gid / G >= io.env_n) return;
+    const long long env = io.env0 + gid / G;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
     const int action = (int)io.actions[env];
     step_env<G, true>(P, io, (int)env, lane, liw, action, lut, env);
@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(kBlock, 6) rollout_kernel(const __grid_constan
         io.reward64 = nullptr;
         io.terminated = term_scratch; io.truncated = trunc_scratch;
         io.terminal_obs = nullptr; io.episodes = nullptr;
+        io.env0 = 0; io.env_n = P.n_envs;
         if (step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env)) {
             const uint32_t episode = P.states[env].episode;
             group_sync<G>(liw);
@@ -292,8 +293,8 @@ __global__ void __launch_bounds__(kBlock) simple_reset_kernel(EngineParams P, co
 template <int G, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) simple_step_kernel(EngineParams P, StepIO io) {
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const long long env = gid / G;
-    if (env >= P.n_envs) return;
+    if (gid / G >= io.env_n) return;
+    const long long env = io.env0 + gid / G;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
     simple_step_env<G>(P, io, (int)env, lane, liw, (int)io.actions[env], env);
 }
@@ -372,6 +373,9 @@ struct nav3d_engine {
     float *d_dist_lut = nullptr;
     int reset_grid = 0;
     cudaStream_t own_stream = nullptr;
+    static constexpr int kHostChunks = 4;          // nav3d_step_host pipeline depth
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done[kHostChunks] = {};
     uint64_t launches = 0;
 };
 
@@ -517,6 +521,10 @@ void nav3d_destroy(nav3d_engine *e) {
     cudaFree(e->d_states); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
     cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_pend_count); cudaFree(e->d_pend_list); cudaFree(e->d_dist_lut);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_stream) {
+        cudaStreamDestroy(e->copy_stream);
+        for (auto &ev : e->chunk_done) if (ev) cudaEventDestroy(ev);
+    }
     delete e;
 }
 
@@ -657,24 +665,18 @@ int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_
     return NAV3D_OK;
 }
 
-int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, double *reward64,
-               uint8_t *terminated, uint8_t *truncated, float *terminal_obs, nav3d_episode *episodes, void *stream) {
-    if (int rc = check_ready(e)) return rc;
-    if (!actions || !obs || !reward || !terminated || !truncated)
-        return fail(NAV3D_ERR_INVALID, "actions, obs, reward, terminated and truncated are required");
-    if (!e->simple && (((uintptr_t)obs & 15u) || (terminal_obs && ((uintptr_t)terminal_obs & 15u))))
-        return fail(NAV3D_ERR_INVALID, "obs / terminal_obs must be 16-byte aligned");
-    NAV3D_DEVICE(e);
-    StepIO io;
-    io.actions = reinterpret_cast<const long long *>(actions);
-    io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = terminated; io.truncated = truncated;
-    io.terminal_obs = terminal_obs; io.episodes = episodes;
-    cudaStream_t s = (cudaStream_t)stream;
+}  // extern "C"
+
+namespace {
+
+// Launch the step of envs [env0, env0 + n) on `s` (the whole engine: env0 = 0, n = n_envs).
+int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
+    io.env0 = env0; io.env_n = n;
     PendingResets pend{e->d_pend_count, e->d_pend_list};
     const int minb = e->minb;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
-        const unsigned grid = grid_for(e->cfg.n_envs, G);
+        const unsigned grid = grid_for(n, G);
         if (e->simple) {
             if (minb == 6) simple_step_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io);
             else simple_step_kernel<G, 8><<<grid, kBlock, 0, s>>>(e->P, io);
@@ -700,8 +702,7 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
             default: step_kernel<G, 1><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
         }
         if (e->P.auto_reset) {
-            const long long max_groups = e->cfg.n_envs;
-            unsigned rgrid = (unsigned)std::min<long long>(e->reset_grid, (max_groups * G + kBlock - 1) / kBlock);
+            unsigned rgrid = (unsigned)std::min<long long>(e->reset_grid, ((long long)n * G + kBlock - 1) / kBlock);
             reset_pending_kernel<G><<<rgrid, kBlock, 0, s>>>(e->P, pend, io.obs);
         }
         return NAV3D_OK;
@@ -712,6 +713,28 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
     return NAV3D_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, double *reward64,
+               uint8_t *terminated, uint8_t *truncated, float *terminal_obs, nav3d_episode *episodes, void *stream) {
+    if (int rc = check_ready(e)) return rc;
+    if (!actions || !obs || !reward || !terminated || !truncated)
+        return fail(NAV3D_ERR_INVALID, "actions, obs, reward, terminated and truncated are required");
+    if (!e->simple && (((uintptr_t)obs & 15u) || (terminal_obs && ((uintptr_t)terminal_obs & 15u))))
+        return fail(NAV3D_ERR_INVALID, "obs / terminal_obs must be 16-byte aligned");
+    NAV3D_DEVICE(e);
+    StepIO io;
+    io.actions = reinterpret_cast<const long long *>(actions);
+    io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = terminated; io.truncated = truncated;
+    io.terminal_obs = terminal_obs; io.episodes = episodes;
+    return launch_step(e, io, 0, e->cfg.n_envs, (cudaStream_t)stream);
+}
+
+// The host-buffer step is a copy pipeline: the envs are cut into chunks; chunk c's actions go up and its step runs on the
+// compute stream while chunk c-1's observations, rewards and flags come down on the copy stream.  The device->host copy of
+// the observations (320 B per env) is what bounds this path (PCIe), so everything else hides behind it.
 int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, uint8_t *terminated,
                     uint8_t *truncated) {
     if (int rc = check_ready(e)) return rc;
@@ -721,16 +744,29 @@ int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *
     const size_t obs_dim = (size_t)e->P.obs_dim;
     if (!e->d_obs) CUDA_TRY(cudaMalloc(&e->d_obs, N * obs_dim * sizeof(float)));
     if (!e->d_actions) CUDA_TRY(cudaMalloc(&e->d_actions, N * sizeof(long long)));
-    cudaStream_t s = e->own_stream;
-    CUDA_TRY(cudaMemcpyAsync(e->d_actions, actions, N * sizeof(long long), cudaMemcpyHostToDevice, s));
-    int rc = nav3d_step(e, reinterpret_cast<const int64_t *>(e->d_actions), e->d_obs, e->d_reward, nullptr, e->d_term,
-                        e->d_trunc, nullptr, nullptr, s);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(obs, e->d_obs, N * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(terminated, e->d_term, N, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(truncated, e->d_trunc, N, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    if (!e->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (auto &ev : e->chunk_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    cudaStream_t sc = e->own_stream, sd = e->copy_stream;
+    // pending-list resets (mode 0) share one list per engine: keep that variant in one piece
+    const int chunks = (N >= 65536 && (e->inline_reset || e->simple)) ? nav3d_engine::kHostChunks : 1;
+    StepIO io;
+    io.actions = e->d_actions; io.obs = e->d_obs; io.reward = e->d_reward; io.reward64 = nullptr;
+    io.terminated = e->d_term; io.truncated = e->d_trunc; io.terminal_obs = nullptr; io.episodes = nullptr;
+    for (int c = 0; c < chunks; c++) {
+        const size_t b0 = N * c / chunks, b1 = N * (c + 1) / chunks, cnt = b1 - b0;
+        CUDA_TRY(cudaMemcpyAsync(e->d_actions + b0, actions + b0, cnt * sizeof(long long), cudaMemcpyHostToDevice, sc));
+        if (int rc = launch_step(e, io, (int)b0, (int)cnt, sc)) return rc;
+        CUDA_TRY(cudaEventRecord(e->chunk_done[c], sc));
+        CUDA_TRY(cudaStreamWaitEvent(sd, e->chunk_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(obs + b0 * obs_dim, e->d_obs + b0 * obs_dim, cnt * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, sd));
+        CUDA_TRY(cudaMemcpyAsync(reward + b0, e->d_reward + b0, cnt * sizeof(float), cudaMemcpyDeviceToHost, sd));
+        CUDA_TRY(cudaMemcpyAsync(terminated + b0, e->d_term + b0, cnt, cudaMemcpyDeviceToHost, sd));
+        CUDA_TRY(cudaMemcpyAsync(truncated + b0, e->d_trunc + b0, cnt, cudaMemcpyDeviceToHost, sd));
+    }
+    CUDA_TRY(cudaStreamSynchronize(sd));
+    CUDA_TRY(cudaStreamSynchronize(sc));
     return NAV3D_OK;
 }
 

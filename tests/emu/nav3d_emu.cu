@@ -100,7 +100,7 @@ void emu_step(void *h, const long long *actions, float *obs, float *reward, doub
     Emu *e = (Emu *)h;
     StepIO io;
     io.actions = actions; io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = term;
-    io.truncated = trunc; io.terminal_obs = terminal_obs; io.episodes = episodes;
+    io.truncated = trunc; io.terminal_obs = terminal_obs; io.episodes = episodes; io.env0 = 0; io.env_n = e->P.n_envs;
     if (e->simple) {
         for (int env = 0; env < e->P.n_envs; env++) simple_step_env<1>(e->P, io, env, 0, 0, (int)actions[env], env);
         return;
