@@ -196,6 +196,46 @@ def test_full_size_sample_against_oracle(oracle):
     assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
 
 
+def test_config3_full_size_sample_against_oracle(oracle):
+    """BASELINE.json configs[2] at its full size: 65 536 envs over the 42 P2+P3 training rooms (heterogeneous sizes, per-env
+    room index), stepped one launch per step with host-chosen random actions; a strided sample of 512 envs is replayed by
+    the oracle under the same global env ids and compared bit-exactly every step; invariants over all envs."""
+    import torch
+    from nav3d import Engine
+    rooms = load_room_dir(ROOMS / "P2_training", sort=True) + load_room_dir(ROOMS / "P3_training", sort=True)
+    n, T, seed = 65536, 320, 31
+    eng = Engine(n, rooms, local_map_length=10, seed=seed)
+    dev = eng.device
+    obs = eng.reset()
+    ids = np.arange(0, n, n // 512, dtype=np.uint32)
+    orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
+    ov = oracle.OracleVec(len(ids), orooms, 10, -2.0, seed, 0, True)
+    ov.set_ids(ids)
+    tid = torch.as_tensor(ids.astype(np.int64), device=dev)
+    assert np.array_equal(obs[tid].cpu().numpy().view(np.uint32), ov.reset().view(np.uint32))
+    rew = torch.zeros(n, device=dev); rew64 = torch.zeros(n, dtype=torch.float64, device=dev)
+    te = torch.zeros(n, dtype=torch.uint8, device=dev); tr = torch.zeros(n, dtype=torch.uint8, device=dev)
+    rng = np.random.default_rng(seed)
+    n_done = 0
+    for t in range(T):
+        a = rng.integers(0, 6, size=n)
+        eng.step(torch.as_tensor(a, device=dev), obs, rew, te, tr, reward64=rew64)
+        ov.step(a[ids])
+        assert np.array_equal(obs[tid].cpu().numpy().view(np.uint32), ov.obs.view(np.uint32)), f"obs t={t}"
+        assert np.array_equal(rew64[tid].cpu().numpy(), ov.reward), f"reward t={t}"
+        assert np.array_equal(te[tid].cpu().numpy(), ov.terminated) and np.array_equal(tr[tid].cpu().numpy(), ov.truncated)
+        n_done += int((ov.terminated | ov.truncated).sum())
+    assert n_done > 0                                       # maze_3d_tunnels (149 steps) and tightcorridor (302) end inside
+    st = eng.get_state()
+    assert np.array_equal(st[tid].cpu().numpy()[:, :15].astype(np.int64), ov.state())
+    rooms_used = torch.unique(st[:, 13]).numel()
+    assert rooms_used == 42
+    free = torch.as_tensor(eng.room_free, device=dev)[st[:, 13].long()]
+    assert bool(((obs >= 0) & (obs <= 1)).all()) and bool((obs[:, 64:68].sum(dim=1) == 1).all()) and bool((obs[:, 73:] == 0).all())
+    assert bool((st[:, 4] <= free).all()) and bool((st[:, 4] >= 1).all()) and bool((st[:, 6] <= T).all())
+    assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
+
+
 @pytest.mark.parametrize("inline,minb", [("0", "8"), ("0", "12"), ("1", "8"), ("2", "8"), ("2", "10")])
 def test_both_reset_paths_and_occupancy_variants(oracle, monkeypatch, inline, minb):
     """Auto-reset has three implementations — out-of-line call in the step kernel (default, mode 2), inlined (1), pending

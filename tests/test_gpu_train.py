@@ -120,7 +120,7 @@ def test_ppo_learns_on_gpu_env(tmp_path):
     assert len(st["r"]) == 8 and (st["total_free"] == 144).all()
 
 
-@pytest.mark.parametrize("S,B,F,H,p_start", [(1, 3, 5, 8, 0.5), (17, 33, 80, 64, 0.15), (128, 512, 80, 256, 0.01), (64, 700, 80, 256, 0.0)])
+@pytest.mark.parametrize("S,B,F,H,p_start", [(1, 3, 5, 8, 0.5), (9, 6, 7, 10, 0.3), (17, 33, 80, 64, 0.15), (128, 512, 80, 256, 0.01), (64, 700, 80, 256, 0.0)])
 def test_fused_lstm_matches_torch_lstm(S, B, F, H, p_start):
     """nav3d_lstm_forward / nav3d_lstm_backward against torch.nn.LSTM stepped one timestep at a time with the state
     zeroed at episode starts (plain fp32, TF32 off on both sides): outputs, final state and all four parameter gradients.
