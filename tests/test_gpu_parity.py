@@ -259,6 +259,56 @@ def test_engine_limits_and_degenerate_rooms(oracle, lanes):
     lockstep(oracle, degenerate_rooms()[3:], n=64, L=10, steps=400, seed=8, lanes=lanes, auto_reset=False)
 
 
+@pytest.mark.parametrize("lanes", [1, 4, 16])
+def test_partial_reset_of_listed_envs(oracle, lanes):
+    """nav3d_reset with env_ids + injected picks (the manual gym-style reset of SOME envs, auto_reset off): the listed envs
+    restart exactly like the reference's reset with those (room, start) draws, every other env is untouched, and all keep
+    stepping in lock-step with one scalar oracle per env."""
+    from gpu_harness import GpuEngine
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_7x7_seed22.txt"), load_room_file(ROOMS / "P2_training" / "tightcorridor.txt"),
+             load_room_file(ROOMS / "P3_training" / "kitchen2.txt")]
+    orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
+    n, L = 48, 10
+    rng = np.random.default_rng(9)
+    g = GpuEngine(n, rooms, L, -2.0, 1, 0, False, lanes)
+    envs = [oracle.OracleCubic(L, -2.0) for _ in range(n)]
+
+    def draw(k):
+        r = rng.integers(0, len(rooms), size=k)
+        return np.stack([r, np.array([rng.integers(0, orooms[i].n_free) for i in r])], axis=1).astype(np.int32)
+
+    picks = draw(n)
+    obs = g.reset(picks=picks)
+    for i in range(n):
+        o = envs[i].reset(orooms[picks[i, 0]], orooms[picks[i, 0]].free_cell(picks[i, 1]))
+        assert np.array_equal(obs[i].view(np.uint32), o.view(np.uint32))
+
+    def lockstep_steps(k):
+        for _ in range(k):
+            a = rng.integers(0, 6, size=n)
+            g.step(a)
+            for i in range(n):
+                o, r, te, tr = envs[i].step(int(a[i]))
+                assert np.array_equal(g.obs[i].view(np.uint32), o.view(np.uint32)) and g.reward64[i] == r
+                assert bool(g.term[i]) == te and bool(g.trunc[i]) == tr
+    lockstep_steps(40)
+    before_state, before_obs = g.state().copy(), g.obs.copy()
+    ids = np.array([40, 3, 17, 41], dtype=np.int32)                 # unordered on purpose
+    p2 = draw(len(ids))
+    obs = g.reset(picks=p2, env_ids=ids)
+    others = np.setdiff1d(np.arange(n), ids)
+    assert np.array_equal(obs[others].view(np.uint32), before_obs[others].view(np.uint32))
+    st = g.state()
+    assert np.array_equal(st[others], before_state[others])
+    for j, i in enumerate(ids):
+        o = envs[i].reset(orooms[p2[j, 0]], orooms[p2[j, 0]].free_cell(p2[j, 1]))
+        assert np.array_equal(obs[i].view(np.uint32), o.view(np.uint32))
+        assert st[i, 6] == 0 and st[i, 4] == 1 and st[i, 13] == p2[j, 0] and st[i, 14] == before_state[i, 14] + 1
+    lockstep_steps(60)
+    for i in (3, 17, 0, 47):
+        assert np.array_equal(g.grid(i), np.minimum(envs[i].grid(), 255).astype(np.int16))
+
+
 def test_snapshot_restore_replays_identically(oracle):
     """nav3d_snapshot / nav3d_restore: the complete mutable state (records + knowledge) round-trips through host memory."""
     import torch
