@@ -114,3 +114,26 @@ def test_furniture_stamps_compose_into_rooms(tmp_path):
     out = tmp_path / "flat.txt"
     assert main(["compose", "--objects", str(ROOMS / "objects"), "--size", "32,32,12", "--count", "5", "-o", str(out)]) == 0
     assert validate_room_file(out).n_free_interior > 0
+
+
+def test_writer_parser_roundtrip_property():
+    """Property (hypothesis): for any grid of 0 / wall cells and any dimensions the writer's text parses back to the same
+    grid in both env conventions, with or without Start/Goal lines, and the validator never raises."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 9), st.integers(1, 9), st.integers(1, 7), st.integers(0, 2 ** 32 - 1), st.booleans())
+    def check(w, d, h, seed, with_start):
+        rng = np.random.default_rng(seed)
+        g = np.where(rng.random((w, d, h)) < 0.4, -2, 0).astype(np.int8)
+        start = (int(rng.integers(w)), int(rng.integers(d)), int(rng.integers(h))) if with_start else None
+        text = room_to_text(g, start, start)
+        room = parse_room_text(text)
+        assert np.array_equal(room.grid, g) and room.start == start and room.goal == start
+        simple = parse_room_text(text, simple=True)
+        assert np.array_equal(simple.grid == 2, g == -2) and simple.wall_code == 2
+        rep = validate_room_text(text)
+        assert rep.dims == (w, d, h) and rep.n_wall == int((g == -2).sum())
+        if min(w, d, h) > 2:
+            assert rep.n_free_interior == int((g[1:-1, 1:-1, 1:-1] != -2).sum())
+    check()
