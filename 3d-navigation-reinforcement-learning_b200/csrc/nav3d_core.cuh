@@ -509,10 +509,14 @@ NAV3D_HD void reset_env_philox(const EngineParams &P, int env, int lane, int lan
 struct EpisodeRec { float episode_return; int32_t length, bumps, visited, total_free, room, terminated, truncated; };
 
 // Returns true when the env finished its episode and must be reset by the caller (auto_reset and !INLINE_RESET).
-template <int G, bool INLINE_RESET>
+// REG_STATE (fused multi-step rollouts): the env's record lives in the caller's registers (`rs`, every lane holds a
+// copy and every lane computes the new one) instead of making a round trip through global memory each step; the
+// terminated / truncated bits come back in `done_bits` and the flag arrays of `io` may be null.
+template <int G, bool INLINE_RESET, bool REG_STATE = false>
 NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
-                       const float *lut, long long row /* row index for the output arrays */) {
-    const EnvState st = P.states[env];
+                       const float *lut, long long row /* row index for the output arrays */, EnvState *rs = nullptr,
+                       uint32_t *done_bits = nullptr) {
+    const EnvState st = REG_STATE ? *rs : P.states[env];
     const RoomDev R = P.rooms[st.room];
     uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
     uint8_t *C = envk + P.c_off;
@@ -581,7 +585,8 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
     if (explored && !will_reset) mark_seen<G>(R, envk, lane, x, y, z, r, (int)dir, P.L);
     if (r.near_wall) flags |= kNearWall;
 
-    if (lane == 0) {
+    if (REG_STATE || lane == 0) {
+        const bool writer = lane == 0;
         // compute_reward (:169-224), same operations in the same order, f64
         double rew = -0.05;
         const double pen = (double)c_new * 0.02;
@@ -602,11 +607,14 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
         if (truncated) { rew += -5.0; cents -= 500; }
         const int ret_centi = st.ret_centi + cents;
 
-        store_stream(io.reward + row, (float)rew);
-        if (io.reward64) io.reward64[row] = rew;
-        io.terminated[row] = done ? 1 : 0;
-        io.truncated[row] = truncated ? 1 : 0;
-        if ((done || truncated) && io.episodes) {
+        if (writer) {
+            store_stream(io.reward + row, (float)rew);
+            if (io.reward64) io.reward64[row] = rew;
+            if (!REG_STATE || io.terminated) io.terminated[row] = done ? 1 : 0;
+            if (!REG_STATE || io.truncated) io.truncated[row] = truncated ? 1 : 0;
+        }
+        if (REG_STATE && done_bits) *done_bits = (done ? 1u : 0u) | (truncated ? 2u : 0u);
+        if (writer && (done || truncated) && io.episodes) {
             EpisodeRec ep;
             ep.episode_return = (float)((double)ret_centi / 100.0 + (double)bump_count * P.crash_penalty);
             ep.length = (int32_t)step_count; ep.bumps = (int32_t)bump_count; ep.visited = (int32_t)visited;
@@ -619,7 +627,8 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
             ns.last_action = (uint8_t)a; ns.flags = (uint8_t)flags; ns.down = (uint8_t)r.down; ns.pad0 = (uint8_t)r.blocked6;
             ns.step_count = step_count; ns.visited_count = visited; ns.bump_count = bump_count;
             ns.ret_centi = ret_centi; ns.episode = st.episode; ns.room = st.room; ns.pad1 = 0;
-            P.states[env] = ns;
+            if (REG_STATE) *rs = ns;
+            else P.states[env] = ns;
         }
     }
     if (INLINE_RESET) {

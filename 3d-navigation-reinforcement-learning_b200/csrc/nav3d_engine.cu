@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(kBlock, 6) rollout_kernel(const __grid_constan
     if (env >= P.n_envs) return;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
     const long long N = P.n_envs;
+    EnvState st = P.states[env];          // the record stays in registers for the whole rollout (every lane holds a copy)
     for (int t = 0; t < T; t++) {
         uint32_t u0, u1;
         philox4x32_10(P.env_id0 + (uint32_t)env, t0 + (uint32_t)t, 0u, kStreamAction, P.seed_lo, P.seed_hi, u0, u1);
@@ -250,20 +251,23 @@ __global__ void __launch_bounds__(kBlock, 6) rollout_kernel(const __grid_constan
         io.obs = obs ? obs + (long long)t * N * kObsDim : (t == T - 1 ? obs_last : nullptr);
         io.reward = reward ? reward + (long long)t * N : reward_scratch;
         io.reward64 = nullptr;
-        io.terminated = term_scratch; io.truncated = trunc_scratch;
+        io.terminated = nullptr; io.truncated = nullptr;
         io.terminal_obs = nullptr; io.episodes = nullptr;
         io.env0 = 0; io.env_n = P.n_envs;
-        if (step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env)) {
-            const uint32_t episode = P.states[env].episode;
-            group_sync<G>(liw);
-            reset_out_of_line<G>(P, (int)env, lane, liw, episode, lut, io.obs ? io.obs + env * kObsDim : nullptr);
+        uint32_t bits = 0;
+        if (step_env<G, false, true>(P, io, (int)env, lane, liw, action, lut, env, &st, &bits)) {
+            group_sync<G>(liw);            // all lanes are done reading the old knowledge
+            reset_out_of_line<G>(P, (int)env, lane, liw, st.episode, lut, io.obs ? io.obs + env * kObsDim : nullptr);
+            group_sync<G>(liw);            // lane 0's record of the new episode is visible
+            st = P.states[env];
         }
         if (lane == 0) {
-            if (done) done[(long long)t * N + env] = term_scratch[env] | trunc_scratch[env];
+            if (done) done[(long long)t * N + env] = bits ? 1 : 0;
             if (actions_out) actions_out[(long long)t * N + env] = (uint8_t)action;
         }
-        group_sync<G>(liw);   // lane 0's state / counter stores and every lane's S stores are visible to the next step
+        group_sync<G>(liw);   // lane 0's counter store and every lane's S stores are visible to the next step
     }
+    if (lane == 0) P.states[env] = st;
 }
 
 template <int G>
