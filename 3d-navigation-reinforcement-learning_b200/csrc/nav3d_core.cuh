@@ -27,6 +27,10 @@
 namespace nav3d {
 
 constexpr int kObsDim = 80;
+// Shared look-up table of the step kernels: [0, 23) (m + 2) / 22 for the window (CubicEnv.py:273-275); [24, 30) k / 5 for
+// last_action (:284); [32, 64) d / L for cells_insight_down when L <= 31 (:287).  All entries are correctly rounded f32
+// quotients, i.e. the same bits as computing them in place.
+constexpr int kLutSize = 64, kLutFifth = 24, kLutDown = 32;
 constexpr uint32_t kStreamReset = 0x52455345u;   // include/nav3d.h "Random streams"
 constexpr uint32_t kStreamAction = 0x41435449u;
 
@@ -199,26 +203,46 @@ struct Rays {
                                // d = 0 +x, 1 -x, 2 +y, 3 -y, 4 +z, 5 -z.  Cached in the record for the next step's move.
 };
 
-// cells p+1 .. p+n along increasing bit index of w
+NAV3D_HD int ffs32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)v);
+#else
+    return v ? __builtin_ctz(v) + 1 : 0;
+#endif
+}
+NAV3D_HD int clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+// cells p+1 .. p+n along increasing bit index of w.  SHORT (ray length <= 31): only the 32 cells next to p can matter, so
+// the scan runs on one 32-bit word (a wall further away reads as "none", which is what f > n means anyway).
+template <bool SHORT>
 NAV3D_HD void ray_up(unsigned long long w, int p, int n, int &ext, int &nfree, int &near) {
     ext = 0; nfree = 0; near = 0;
     if (n <= 0) return;
     unsigned long long m = w >> (p + 1);                 // n > 0 implies p + 1 <= 63
-    int f = ffs64(m);                                    // 1-based distance of the first wall, 0 = none
+    int f = SHORT ? ffs32((uint32_t)m) : ffs64(m);       // 1-based distance of the first wall, 0 = none
     if (f != 0 && f <= n) { ext = f; nfree = f - 1; near = (f == 1); }
     else { ext = n; nfree = n; }
 }
 // cells p-1 .. p-n along decreasing bit index of w
+template <bool SHORT>
 NAV3D_HD void ray_down(unsigned long long w, int p, int n, int &ext, int &nfree, int &near) {
     ext = 0; nfree = 0; near = 0;
     if (n <= 0) return;                                  // n > 0 implies 1 <= p <= 63
     unsigned long long m = w << (64 - p);                // bit 63 = cell p-1
-    int f = m ? clz64(m) + 1 : 0;
+    int f;
+    if (SHORT) { const uint32_t hi = (uint32_t)(m >> 32); f = hi ? clz32(hi) + 1 : 0; }
+    else f = m ? clz64(m) + 1 : 0;
     if (f != 0 && f <= n) { ext = f; nfree = f - 1; near = (f == 1); }
     else { ext = n; nfree = n; }
 }
 
-NAV3D_HD Rays cast_rays(const EngineParams &P, const RoomDev &R, int x, int y, int z) {
+template <bool SHORT>
+NAV3D_HD Rays cast_rays_t(const EngineParams &P, const RoomDev &R, int x, int y, int z) {
     const int L = P.L, W = R.W, D = R.D, H = R.H;
     unsigned long long wx = ldg(P.occ64 + R.occx_off + (uint32_t)(y * H + z));
     unsigned long long wy = ldg(P.occ64 + R.occy_off + (uint32_t)(x * H + z));
@@ -226,18 +250,21 @@ NAV3D_HD Rays cast_rays(const EngineParams &P, const RoomDev &R, int x, int y, i
     Rays r;
     int ext, nfree, near, any = 0, n;
     uint32_t blk = 0;
-    n = imin(L, W - 1 - x); ray_up(wx, x, n, ext, nfree, near);   r.x1 = x + ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 0;
-    n = imin(L, x);         ray_down(wx, x, n, ext, nfree, near); r.x0 = x - ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 1;
-    n = imin(L, D - 1 - y); ray_up(wy, y, n, ext, nfree, near);   r.y1 = y + ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 2;
-    n = imin(L, y);         ray_down(wy, y, n, ext, nfree, near); r.y0 = y - ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 3;
+    n = imin(L, W - 1 - x); ray_up<SHORT>(wx, x, n, ext, nfree, near);   r.x1 = x + ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 0;
+    n = imin(L, x);         ray_down<SHORT>(wx, x, n, ext, nfree, near); r.x0 = x - ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 1;
+    n = imin(L, D - 1 - y); ray_up<SHORT>(wy, y, n, ext, nfree, near);   r.y1 = y + ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 2;
+    n = imin(L, y);         ray_down<SHORT>(wy, y, n, ext, nfree, near); r.y0 = y - ext; any |= near; blk |= (uint32_t)(near | (n <= 0)) << 3;
     int zu, zd;
-    n = imin(L, H - 1 - z); ray_up(wz, z, n, zu, nfree, near);    any |= near; blk |= (uint32_t)(near | (n <= 0)) << 4;
-    n = imin(L, z);         ray_down(wz, z, n, zd, nfree, near);  any |= near; blk |= (uint32_t)(near | (n <= 0)) << 5;
+    n = imin(L, H - 1 - z); ray_up<SHORT>(wz, z, n, zu, nfree, near);    any |= near; blk |= (uint32_t)(near | (n <= 0)) << 4;
+    n = imin(L, z);         ray_down<SHORT>(wz, z, n, zd, nfree, near);  any |= near; blk |= (uint32_t)(near | (n <= 0)) << 5;
     r.down = nfree;
     r.zmask = ((2u << (z + zu)) - 1u) & ~((1u << (z - zd)) - 1u);
     r.near_wall = any;
     r.blocked6 = blk;
     return r;
+}
+NAV3D_HD Rays cast_rays(const EngineParams &P, const RoomDev &R, int x, int y, int z) {
+    return P.L <= 31 ? cast_rays_t<true>(P, R, x, y, z) : cast_rays_t<false>(P, R, x, y, z);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -361,7 +388,8 @@ NAV3D_HD void window_store(const RoomDev &R, int lane, int x, int y, int z, int 
 
 // Steps 3-6 of get_obs: the 9 scalars + zero padding = 4 more float4 (:279-307)
 template <int G>
-NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &sc, float *__restrict__ obs_row) {
+NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &sc, const float *lut,
+                            float *__restrict__ obs_row) {
     for (int j = 16 + lane; j < 20; j += G) {
         float4 v;
         if (j == 16) {
@@ -370,10 +398,11 @@ NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &s
         } else if (j == 17) {
             // float(k)/5, count/L and visited/total are f64 quotients rounded to f32 in the reference (:284-291); for
             // integers below 2^24 that equals the correctly rounded f32 quotient (53 >= 2*24+2, Figueroa 1995).
-            v.x = fdiv_rn((float)sc.last_action, 5.0f);
+            // (the two small quotients come from the shared table: same correctly rounded bits, no division sequence)
+            v.x = lut[kLutFifth + sc.last_action];
             v.y = (float)sc.was_near_wall;
             v.z = (float)sc.last_bump;
-            v.w = fdiv_rn((float)sc.down, (float)P.L);
+            v.w = P.L <= 31 ? lut[kLutDown + sc.down] : fdiv_rn((float)sc.down, (float)P.L);
         } else if (j == 18) {
             v.x = fdiv_rn((float)sc.visited, (float)sc.total_free);
             v.y = v.z = v.w = 0.f;
@@ -449,7 +478,7 @@ NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, in
             window_load<G>(P, R, envk, lane, x, y, z, a0, wb);
             window_store<G>(R, lane, x, y, z, a0, wb, r, centre_count, lut, obs_row);
         }
-        write_scalars<G>(P, lane, sc, obs_row);
+        write_scalars<G>(P, lane, sc, lut, obs_row);
     }
     if (write_seen) mark_seen<G>(R, envk, lane, x, y, z, r, -1, P.L);
 }
@@ -577,7 +606,7 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
             window_load<G>(P, R, envk, lane, x, y, z, a0, wb);
             window_store<G>(R, lane, x, y, z, a0, wb, r, c_new, lut, orow);
         }
-        write_scalars<G>(P, lane, sc, orow);
+        write_scalars<G>(P, lane, sc, lut, orow);
     }
     // The cells a ray pass marks depend only on the position (L and the room are fixed), and marks are never erased
     // within an episode: every earlier stay at this cell (c_old >= 1, which includes every bump) already marked
@@ -675,12 +704,12 @@ NAV3D_HD void simple_observe(const EngineParams &P, const RoomDev &R, uint32_t *
         nf6 |= (unsigned long long)nfree << (8 * (a));                                                      \
         wall6 |= (uint32_t)(ext > nfree) << (a);                     /* a wall stopped the ray (:321-324) */ \
         blk6 |= (uint32_t)((ext > nfree) || (nfree == room_left && nfree < L)) << (a);   /* ... or the room ended (:311-319) */
-        NAV3D_SIMPLE_RAY(0, ray_up(wx, x, imin(L, room_left), ext, nfree, near), W - 1 - x)
-        NAV3D_SIMPLE_RAY(1, ray_down(wx, x, imin(L, room_left), ext, nfree, near), x)
-        NAV3D_SIMPLE_RAY(2, ray_up(wy, y, imin(L, room_left), ext, nfree, near), D - 1 - y)
-        NAV3D_SIMPLE_RAY(3, ray_down(wy, y, imin(L, room_left), ext, nfree, near), y)
-        NAV3D_SIMPLE_RAY(4, ray_up(wz, z, imin(L, room_left), ext, nfree, near), H - 1 - z)
-        NAV3D_SIMPLE_RAY(5, ray_down(wz, z, imin(L, room_left), ext, nfree, near), z)
+        NAV3D_SIMPLE_RAY(0, ray_up<false>(wx, x, imin(L, room_left), ext, nfree, near), W - 1 - x)
+        NAV3D_SIMPLE_RAY(1, ray_down<false>(wx, x, imin(L, room_left), ext, nfree, near), x)
+        NAV3D_SIMPLE_RAY(2, ray_up<false>(wy, y, imin(L, room_left), ext, nfree, near), D - 1 - y)
+        NAV3D_SIMPLE_RAY(3, ray_down<false>(wy, y, imin(L, room_left), ext, nfree, near), y)
+        NAV3D_SIMPLE_RAY(4, ray_up<false>(wz, z, imin(L, room_left), ext, nfree, near), H - 1 - z)
+        NAV3D_SIMPLE_RAY(5, ray_down<false>(wz, z, imin(L, room_left), ext, nfree, near), z)
 #undef NAV3D_SIMPLE_RAY
         (void)near;
     }

@@ -31,9 +31,13 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(NAV3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
     } while (0)
 
-__device__ __forceinline__ void fill_lut(float *lut) {
-    // (m + 2) / 22 in f32 for m = -2 .. 20 (CubicEnv.py:273-275), correctly rounded like NumPy's f32 divide
-    if (threadIdx.x < 23) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 22.0f);
+__device__ __forceinline__ void fill_lut(float *lut, int L) {
+    // nav3d_core.cuh kLut*: (m + 2) / 22 for m = -2 .. 20 (CubicEnv.py:273-275), k / 5 (:284), d / L (:287); correctly
+    // rounded f32 quotients like NumPy's
+    const int t = threadIdx.x;
+    if (t < 23) lut[t] = __fdiv_rn((float)t, 22.0f);
+    else if (t >= kLutFifth && t < kLutFifth + 6) lut[t] = __fdiv_rn((float)(t - kLutFifth), 5.0f);
+    else if (t >= kLutDown && t < kLutSize) lut[t] = __fdiv_rn((float)(t - kLutDown), (float)L);
     __syncthreads();
 }
 
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(256) pack_rooms_kernel(const int8_t *__restric
 template <int G>
 __global__ void __launch_bounds__(kBlock) reset_kernel(EngineParams P, const int32_t *__restrict__ env_ids, int n,
                                                        const int32_t *__restrict__ picks, float *obs) {
-    __shared__ float lut[24];
-    fill_lut(lut);
+    __shared__ float lut[kLutSize];
+    fill_lut(lut, P.L);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
     const long long idx = gid / G;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
@@ -141,8 +145,8 @@ struct PendingResets {
 
 template <int G, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) step_kernel(EngineParams P, StepIO io, PendingResets pend) {
-    __shared__ float lut[24];
-    fill_lut(lut);
+    __shared__ float lut[kLutSize];
+    fill_lut(lut, P.L);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (gid / G >= io.env_n) return;
     const long long env = io.env0 + gid / G;
@@ -171,8 +175,8 @@ __device__ __noinline__ void reset_out_of_line(const EngineParams &P, int env, i
 
 template <int G, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_constant__ EngineParams P, StepIO io) {
-    __shared__ float lut[24];
-    fill_lut(lut);
+    __shared__ float lut[kLutSize];
+    fill_lut(lut, P.L);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (gid / G >= io.env_n) return;
     const long long env = io.env0 + gid / G;
@@ -189,8 +193,8 @@ __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_co
 // costs more than the extra registers.
 template <int G>
 __global__ void __launch_bounds__(kBlock) step_inline_kernel(EngineParams P, StepIO io) {
-    __shared__ float lut[24];
-    fill_lut(lut);
+    __shared__ float lut[kLutSize];
+    fill_lut(lut, P.L);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (gid / G >= io.env_n) return;
     const long long env = io.env0 + gid / G;
@@ -201,9 +205,9 @@ __global__ void __launch_bounds__(kBlock) step_inline_kernel(EngineParams P, Ste
 
 template <int G>
 __global__ void __launch_bounds__(kBlock) reset_pending_kernel(EngineParams P, PendingResets pend, float *obs) {
-    __shared__ float lut[24];
+    __shared__ float lut[kLutSize];
     __shared__ unsigned n_sh;
-    fill_lut(lut);
+    fill_lut(lut, P.L);
     if (threadIdx.x == 0) n_sh = *((volatile unsigned int *)pend.count);
     __syncthreads();
     const unsigned n = n_sh;
@@ -233,8 +237,8 @@ __global__ void __launch_bounds__(kBlock, 6) rollout_kernel(const __grid_constan
                                                             float *obs, float *obs_last, float *reward, uint8_t *done,
                                                             uint8_t *actions_out, float *reward_scratch,
                                                             uint8_t *term_scratch, uint8_t *trunc_scratch) {
-    __shared__ float lut[24];
-    fill_lut(lut);
+    __shared__ float lut[kLutSize];
+    fill_lut(lut, P.L);
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
     const long long env = gid / G;
     if (env >= P.n_envs) return;

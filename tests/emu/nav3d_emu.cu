@@ -19,7 +19,7 @@ struct Emu {
     std::vector<uint32_t> free_cells;
     std::vector<EnvState> states;
     std::vector<uint8_t> know;
-    float lut[24];
+    float lut[nav3d::kLutSize];
     std::vector<float> dist_lut;
     bool simple = false;
 };
@@ -69,6 +69,8 @@ void *emu_create(int n_envs, int L, double crash, unsigned long long seed, unsig
     e->states.assign((size_t)n_envs, EnvState{});
     e->know.assign(stride * (size_t)n_envs, 0xAB);     // poison: a reset must clear what it uses
     for (int i = 0; i < 23; i++) e->lut[i] = (float)i / 22.0f;
+    for (int i = 0; i < 6; i++) e->lut[nav3d::kLutFifth + i] = (float)i / 5.0f;
+    for (int i = 0; i < 32; i++) e->lut[nav3d::kLutDown + i] = (float)i / (float)L;
     EngineParams &P = e->P;
     P.rooms = e->rooms.data(); P.occz = e->occz.data(); P.occ64 = e->occ64.data(); P.free_cells = e->free_cells.data();
     P.states = e->states.data(); P.know = e->know.data(); P.env_stride = stride; P.c_off = (uint32_t)c_off;

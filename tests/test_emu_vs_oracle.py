@@ -48,7 +48,7 @@ def test_emu_heterogeneous_rooms(oracle):
     assert n_done > 0          # maze_3d_tunnels (149 free) and tightcorridor (302) truncate early
 
 
-@pytest.mark.parametrize("L", [1, 4, 15])
+@pytest.mark.parametrize("L", [1, 4, 15, 40])
 def test_emu_ray_lengths(oracle, L):
     rooms = [load_room_file(ROOMS / "P3_training" / "maze_7x7_seed22.txt"), load_room_file(ROOMS / "P3_training" / "kitchen2.txt"),
              load_room_file(ROOMS / "P2_training" / "small_bedroom.txt")]

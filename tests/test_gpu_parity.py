@@ -61,7 +61,7 @@ def test_config3_heterogeneous_p2_p3(oracle):
     assert n_done > 0
 
 
-@pytest.mark.parametrize("L,lanes", [(1, 8), (4, 32), (15, 4)])
+@pytest.mark.parametrize("L,lanes", [(1, 8), (4, 32), (15, 4), (40, 4), (31, 2), (32, 1)])
 def test_ray_lengths_and_crash_penalty(oracle, L, lanes):
     rooms = [load_room_file(ROOMS / "P3_training" / "maze_7x7_seed22.txt"), load_room_file(ROOMS / "P3_training" / "kitchen2.txt"),
              load_room_file(ROOMS / "P2_training" / "small_bedroom.txt"), load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt")]
