@@ -1,12 +1,15 @@
 #!/bin/bash
 # End-to-end demonstration of BASELINE configs[4] on one GPU: train/Grid_Train.py (--native shape, 1024 envs) on
 # rooms/P1_training for STEPS env steps, then evaluate the final checkpoint on rooms/P1_evaluate and run
-# train/evaluate_grid.py over all checkpoints.  usage: tools/train_demo.sh [STEPS] [OUTDIR]
+# train/evaluate_grid.py over all checkpoints.  usage: [NPROC=8] tools/train_demo.sh [STEPS] [OUTDIR]
+# NPROC > 1: data parallel under torchrun (one rank per GPU, NCCL gradient all-reduce); evaluate_grid.py is skipped.
 STEPS=${1:-30000000}
 OUT=${2:-gpurun_out/demo}
 rm -rf "$OUT"; mkdir -p "$OUT"
 T0=$(date +%s.%N)
-python -m train.Grid_Train --native --num-envs 1024 --steps "$STEPS" --save-dir "$OUT/ckpt" \
+NPROC=${NPROC:-1}
+if [ "$NPROC" -gt 1 ]; then LAUNCH="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NPROC --master-addr 127.0.0.1 --master-port 29520 -m train.Grid_Train"; else LAUNCH="python -m train.Grid_Train"; fi
+$LAUNCH --native --num-envs 1024 --steps "$STEPS" --save-dir "$OUT/ckpt" \
     --eval-freq ${EVAL_FREQ:-5000000} > "$OUT/train.log" 2>&1
 echo "train wall $(python -c "import time; print(round(time.time() - $T0, 1))") s" >> "$OUT/train.log"
 grep -E "^\| iter" "$OUT/train.log" | awk 'NR % 20 == 1' | cut -c1-150
@@ -25,6 +28,8 @@ for f in (files[0], files[len(files) // 2], files[-1]):
     env.close()
     print("P1_evaluate", os.path.basename(f)[-24:], {k: round(v, 2) for k, v in agg.items()})
 PY
+if [ "$NPROC" -le 1 ]; then
 python -m train.evaluate_grid --models-dir "$OUT/ckpt" --episodes 10 --txt "$OUT/exp3_viewDistance.txt" --csv "$OUT/exp3_viewDistance.csv" > "$OUT/eval.log" 2>&1
 cat "$OUT/exp3_viewDistance.txt" | cut -c1-140
+fi
 rm -rf "$OUT/ckpt"
