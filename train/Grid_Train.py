@@ -5,7 +5,7 @@ cadence and checkpoint names), with ``SubprocVecEnv`` + sb3-contrib replaced by 
 ``nav3d.ppo.RecurrentPPO``:
 
     python -m train.Grid_Train                      # the reference's constants (8 envs, n_steps 2048, batch 64)
-    python -m train.Grid_Train --native             # B200-sized rollouts: 4096 envs x 128 steps, 64 Ki-transition minibatches
+    python -m train.Grid_Train --native             # B200-sized rollouts: 1024 envs x 128 steps, 64 Ki-transition minibatches
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 -m train.Grid_Train --native   # data parallel
 
 Deviations, all deliberate: ``STEPS_PHASE`` has an entry for every phase (the reference's only active phase has none and
@@ -47,14 +47,14 @@ lstm_sizes = [dict(lstm_hidden_size=256, n_lstm_layers=1)]
 ppo_hparam_sets = [dict(learning_rate=3e-4, n_steps=2048, batch_size=64, gamma=0.99, gae_lambda=0.95, ent_coef=0.01,
                         vf_coef=0.5, clip_range=0.2, n_epochs=10)]
 NATIVE_OVERRIDES = dict(n_steps=128, batch_size=512 * 128)      # --native: 512 envs x 128 steps per minibatch
-NATIVE_NUM_ENVS = 4096
+NATIVE_NUM_ENVS = 1024              # the shape of profiles/train_demo_r01 (100 % finished on P1_evaluate after 72 M steps)
 NATIVE_EVAL_FREQ = 5_000_000        # at ~1e6 steps/s an evaluation every 100 k steps would dominate the run
 
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--native", action="store_true", help="B200-sized rollout/minibatch shape instead of the reference's")
-    ap.add_argument("--num-envs", type=int, default=0, help="envs per GPU (default 8, or 4096 with --native)")
+    ap.add_argument("--num-envs", type=int, default=0, help="envs per GPU (default 8, or 1024 with --native)")
     ap.add_argument("--steps", type=int, default=0, help="override the steps of every phase")
     ap.add_argument("--save-dir", default=SAVE_DIR)
     ap.add_argument("--eval-freq", type=int, default=0, help="steps between evaluations (default 100000; 5000000 with --native)")
