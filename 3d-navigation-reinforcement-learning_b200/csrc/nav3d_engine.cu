@@ -176,7 +176,12 @@ __device__ __noinline__ void reset_out_of_line(const EngineParams &P, int env, i
 template <int G, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_constant__ EngineParams P, StepIO io) {
     __shared__ float lut[kLutSize];
+    // Programmatic dependent launch: when launched with the stream-serialisation attribute this grid may become resident
+    // while the previous kernel of the stream is still draining; everything up to the wait (table fill, index math) overlaps
+    // that tail, and the next kernel is allowed to do the same with ours.  Without the attribute both are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;");
     fill_lut(lut, P.L);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (gid / G >= io.env_n) return;
     const long long env = io.env0 + gid / G;
@@ -378,6 +383,7 @@ struct nav3d_engine {
     bool inline_reset = false;  // small batches: one launch per step with the reset inlined
     int reset_mode = 0;         // 0 pending list + second kernel, 1 inlined, 2 out-of-line call in the same kernel
     bool simple = false;        // NAV3D_ENV_SIMPLE
+    bool pdl = true;            // programmatic dependent launch of the step kernel (NAV3D_PDL=0 switches it off)
     float *d_dist_lut = nullptr;
     int reset_grid = 0;
     cudaStream_t own_stream = nullptr;
@@ -473,6 +479,7 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     e->reset_mode = 2;
     if (const char *ir = getenv("NAV3D_INLINE_RESET")) { e->reset_mode = atoi(ir); e->inline_reset = e->reset_mode != 0; }
     if (const char *mb = getenv("NAV3D_MINB")) e->minb = atoi(mb);
+    if (const char *pd = getenv("NAV3D_PDL")) e->pdl = atoi(pd) != 0;
     // Every global access of the step is a scattered 32-byte sector; the default 64-byte L2 fetch granularity would read
     // twice the bytes from HBM (measured: profiles/step_kernel_r01_v0_details.csv).  This is a hint; failure is harmless.
     if (!getenv("NAV3D_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
@@ -692,10 +699,16 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
         }
         if (e->inline_reset) {
             if (e->reset_mode == 2) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
+                cfg.attrs = attr; cfg.numAttrs = 1;
                 switch (minb) {
-                    case 6: step_call_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io); break;
-                    case 10: step_call_kernel<G, 10><<<grid, kBlock, 0, s>>>(e->P, io); break;
-                    default: step_call_kernel<G, 8><<<grid, kBlock, 0, s>>>(e->P, io); break;
+                    case 6: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 6>, e->P, io); break;
+                    case 10: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 10>, e->P, io); break;
+                    default: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 8>, e->P, io); break;
                 }
             } else step_inline_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
             return NAV3D_OK;
