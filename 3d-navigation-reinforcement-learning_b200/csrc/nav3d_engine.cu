@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(kBlock) simple_reset_kernel(EngineParams P, co
 
 template <int G, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) simple_step_kernel(EngineParams P, StepIO io) {
+    asm volatile("griddepcontrol.launch_dependents;");
     const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent launch, as in step_call_kernel
     if (gid / G >= io.env_n) return;
     const long long env = io.env0 + gid / G;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
@@ -692,19 +694,19 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         const unsigned grid = grid_for(n, G);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
         if (e->simple) {
-            if (minb == 6) simple_step_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io);
-            else simple_step_kernel<G, 8><<<grid, kBlock, 0, s>>>(e->P, io);
+            if (minb == 6) cudaLaunchKernelEx(&cfg, simple_step_kernel<G, 6>, e->P, io);
+            else cudaLaunchKernelEx(&cfg, simple_step_kernel<G, 8>, e->P, io);
             return NAV3D_OK;
         }
         if (e->inline_reset) {
             if (e->reset_mode == 2) {
-                cudaLaunchConfig_t cfg{};
-                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
-                cfg.attrs = attr; cfg.numAttrs = 1;
                 switch (minb) {
                     case 6: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 6>, e->P, io); break;
                     case 10: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 10>, e->P, io); break;

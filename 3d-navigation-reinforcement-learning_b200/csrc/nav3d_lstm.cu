@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_step_kernel(float *__restrict__ 
                                                             int B, int H, float *__restrict__ h_t, float *__restrict__ c_t,
                                                             float *__restrict__ h_in_next) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // launched with programmatic stream serialisation (see pdl_launch)
     if (idx >= B * H) return;
     const int b = idx / H, j = idx - b * H;
     float *g4 = gates_t + (size_t)b * 4 * H;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(float *__restrict__ 
                                                             const uint8_t *__restrict__ starts_t,
                                                             const uint8_t *__restrict__ starts_next, int first, int B, int H) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (idx >= B * H) return;
     const int b = idx / H, j = idx - b * H;
     float *g4 = gates_t + (size_t)b * 4 * H;
@@ -144,6 +146,19 @@ int get_handle(void *stream, cublasHandle_t *out) {
 
 unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
 
+// The per-timestep kernels sit between cuBLAS GEMMs in a chain of ~10 us links: launched with programmatic stream
+// serialisation their blocks become resident while the GEMM before them drains and wait in griddepcontrol.wait.
+template <typename... KArgs, typename... Args>
+cudaError_t pdl_launch(void (*kernel)(KArgs...), unsigned grid, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace
 
 extern "C" {
@@ -171,10 +186,9 @@ int nav3d_lstm_forward(const float *x, const float *w_ih, const float *w_hh, con
         CUBLAS_TRY(cublasSgemm(hnd, CUBLAS_OP_T, CUBLAS_OP_N, G4, B, H, &one, w_hh, H, h_in + (size_t)t * BH, H, &one, g_t, G4));
         const float *c_prev = t == 0 ? c0 : c_all + (size_t)(t - 1) * BH;
         const bool last = t == S - 1;
-        lstm_fwd_step_kernel<<<blocks_for(BH), 256, 0, s>>>(g_t, b_ih, b_hh, c_prev, starts + (size_t)t * B,
-                                                            last ? nullptr : starts + (size_t)(t + 1) * B, B, H,
-                                                            h_all + (size_t)t * BH, c_all + (size_t)t * BH,
-                                                            last ? nullptr : h_in + (size_t)(t + 1) * BH);
+        pdl_launch(lstm_fwd_step_kernel, blocks_for(BH), s, g_t, b_ih, b_hh, c_prev, starts + (size_t)t * B,
+                   last ? nullptr : starts + (size_t)(t + 1) * B, B, H, h_all + (size_t)t * BH, c_all + (size_t)t * BH,
+                   last ? nullptr : h_in + (size_t)(t + 1) * BH);
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nav3d::fail_with(NAV3D_ERR_CUDA, std::string("nav3d_lstm_forward: ") + cudaGetErrorString(err));
@@ -199,9 +213,9 @@ int nav3d_lstm_backward(const float *x, const float *w_hh, const float *c0, cons
         float *g_t = gates + (size_t)t * B * G4;
         const float *c_prev = t == 0 ? c0 : c_all + (size_t)(t - 1) * BH;
         const bool first = t == S - 1;
-        lstm_bwd_step_kernel<<<blocks_for(BH), 256, 0, s>>>(g_t, dh_all + (size_t)t * BH, dh_rec, dc_rec,
-                                                            c_all + (size_t)t * BH, c_prev, starts + (size_t)t * B,
-                                                            first ? nullptr : starts + (size_t)(t + 1) * B, first ? 1 : 0, B, H);
+        pdl_launch(lstm_bwd_step_kernel, blocks_for(BH), s, g_t, dh_all + (size_t)t * BH, dh_rec, dc_rec,
+                   c_all + (size_t)t * BH, c_prev, starts + (size_t)t * B, first ? nullptr : starts + (size_t)(t + 1) * B,
+                   first ? 1 : 0, B, H);
         // dh_rec[B, H] = dgates_t[B, 4H] @ W_hh[4H, H]
         if (t > 0) CUBLAS_TRY(cublasSgemm(hnd, CUBLAS_OP_N, CUBLAS_OP_N, H, B, G4, &one, w_hh, H, g_t, G4, &zero, dh_rec, H));
     }
