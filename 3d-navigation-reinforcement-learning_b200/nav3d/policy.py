@@ -16,9 +16,11 @@ restates the published architecture of ``RecurrentActorCriticPolicy`` rather tha
 
 Parameter names match sb3-contrib's ``state_dict`` keys, so a checkpoint's ``policy.pth`` has the layout SB3 users expect.
 
-The GEMMs run in torch (cuBLAS/cuDNN on the tensor cores); the env step is the hand-written CUDA path.  A sequence is
-processed with cuDNN's fused LSTM over every stretch of timesteps that contains no episode start, so the per-step Python
-loop SB3 falls back to whenever a rollout contains a reset is avoided."""
+The MLP GEMMs run in torch (cuBLAS on the tensor cores); the env step is the hand-written CUDA path.  On a CUDA device a
+sequence goes through the library's fused LSTM (``nav3d_lstm_forward/backward``: cuBLAS GEMMs + one hand-written kernel per
+timestep, the episode-start mask as an operand), with the critic branch on a second stream; single steps, CPU tensors and
+multi-layer LSTMs use ``torch.nn.LSTM`` over every stretch of timesteps that contains no episode start — either way the
+per-step Python loop SB3 falls back to whenever a rollout contains a reset is avoided."""
 from __future__ import annotations
 
 import math

@@ -19,8 +19,9 @@ third-party and un-vendored; what is restated here is its published algorithm:
   minibatch over a flat gradient buffer — the only collective of the whole training loop.
 
 What differs from SB3 on purpose: minibatches are built from whole sequence chunks of many envs (so a minibatch is a few
-large cuDNN/cuBLAS calls), sampling uses the engine's Philox streams (results independent of the shard count), and
-episode statistics are reduced on the device."""
+large GEMM calls), sampling uses the engine's Philox streams (results independent of the shard count), episode statistics
+are reduced on the device, a rollout is replayed as CUDA graphs from the second one on, and minibatches small enough to be
+launch-bound are replayed as one CUDA graph each."""
 from __future__ import annotations
 
 import io
