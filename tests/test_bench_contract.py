@@ -1,0 +1,52 @@
+"""bench.py's output contract: the committed GPU line (profiles/bench_r01_v8.json, produced on a B200) and a live run of the
+reference arm on this machine's cores carry every key the driver reads, with consistent values."""
+import json
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def check_common(d):
+    assert d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True
+    for k in ("value", "ms_per_step"):
+        assert isinstance(d[k], float) and d[k] > 0
+    for k in ("n_gpus", "steps", "warmup"):
+        assert isinstance(d[k], int) and d[k] >= 1
+    assert d["warmup"] >= 3 and d["scaling"] in ("weak", "strong") and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == d["unit"] and "h2d_bytes_per_step" in e and "d2h_bytes_per_step" in e
+    c = d["cpu_baseline"]
+    assert c["value"] > 0 and c["unit"] == d["unit"] and c["cores"] >= 1 and c["kind"] in ("port", "reference") and c["sample"]
+
+
+def test_committed_gpu_line_has_the_contract_keys():
+    d = json.loads((ROOT / "profiles" / "bench_r01_v8.json").read_text().strip().splitlines()[-1])
+    check_common(d)
+    assert d["n_gpus"] == 1 and d["gpu_launches"] == d["steps"]                 # one nav3d_step launch per timed step
+    assert d["e2e"]["h2d_bytes_per_step"] == 8 << 20 and d["e2e"]["d2h_bytes_per_step"] == (1 << 20) * (320 + 4 + 1 + 1)
+    assert d["e2e"]["value"] < d["value"]                                        # host copies inside the timed region
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["algorithmic_bytes_per_env_step"] == 592 and r["env_steps_per_launch"] == 1 << 20
+    assert abs(r["achieved"] - 592 * (1 << 20) / (r["launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert abs(d["value"] - (1 << 20) / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    assert isinstance(r["traffic"], int) and r["traffic"] > 592 * (1 << 20)      # real DRAM bytes exceed the algorithmic ones
+    traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text())["c4_dram_bytes_per_launch"]
+    assert traffic > 0
+    c = d["clocks"]
+    assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert {"c2", "c3", "c5_train", "simple_env", "fused_rollout_c4"} <= set(d["extra"])
+
+
+def test_reference_arm_runs_on_host_cores():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0
+    check_common(d)
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert 1e3 < d["value"] < 1e7                                               # a Python env: thousands of steps/s per core
