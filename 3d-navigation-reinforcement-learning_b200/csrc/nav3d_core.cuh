@@ -36,7 +36,6 @@ constexpr uint32_t kStreamAction = 0x41435449u;
 
 // flag bits of EnvState::flags
 constexpr uint32_t kNearWall = 1u, kWasNearWall = 2u, kLastBump = 4u, kDone = 8u;
-constexpr uint32_t kSColValid = 16u;   // EngineParams::scol of this env holds the S words of the window around (x, y)
 
 struct alignas(32) RoomDev {       // one per room, read-only after nav3d_load_rooms
     uint16_t W, D, H, ntx;         // dims; ntx = ceil(W/4) tiles along x
@@ -65,11 +64,6 @@ struct EngineParams {
     const unsigned long long *occ64;
     const uint32_t *free_cells;
     EnvState *states;
-    // Per env, the S words of the 16 columns of the 4x4 window around the agent as of its last observation, in torus order
-    // (slot = (cx & 3) * 4 + (cy & 3)): 32 bytes that stream with the record.  After a move only the four entering columns
-    // are fetched from the S tiles; a bump or a vertical move fetches none (tools/atom_model.py: 2.2 -> 0.9 scattered
-    // 64-byte atoms per step).  NULL = feature off (simpleEnv).
-    uint16_t *scol;
     uint8_t *know;                 // per-env knowledge storage: [S tiles | C bricks]
     unsigned long long env_stride; // bytes per env in `know`
     uint32_t c_off;                // byte offset of the C bricks inside an env block
@@ -315,7 +309,7 @@ template <int G> struct WinBatch {                 // what one batch of window l
 // c_index), computed once per a / per b.
 template <int G>
 NAV3D_HD void window_load(const EngineParams &P, const RoomDev &R, const uint8_t *envk, int lane, int x, int y, int z,
-                          int a0, WinBatch<G> &wb, const uint16_t *scol, bool scol_valid, int px, int py) {
+                          int a0, WinBatch<G> &wb) {
     using M = WinMap<G>;
     const uint16_t *__restrict__ S = reinterpret_cast<const uint16_t *>(envk);
     const uint8_t *__restrict__ C = envk + P.c_off;
@@ -339,9 +333,7 @@ NAV3D_HD void window_load(const EngineParams &P, const RoomDev &R, const uint8_t
             wb.inb[a][b] = in;
             wb.sw[a][b] = 0; wb.ow[a][b] = 0; wb.cw[a][b] = 0;
             if (in) {
-                // a column that was in the window of the last observation (centre (px, py)) comes from the streamed copy
-                const bool hit = scol_valid && (unsigned)(cx - px + 2) < 4u && (unsigned)(cy - py + 2) < 4u;
-                wb.sw[a][b] = hit ? scol[((cx & 3) << 2) | (cy & 3)] : S[xs + (cy >> 2) * ntx16 + (cy & 3)];
+                wb.sw[a][b] = S[xs + (cy >> 2) * ntx16 + (cy & 3)];
                 wb.ow[a][b] = ldg(P.occz + R.occz_off + (uint32_t)(xo + cy));
                 const uint16_t *cp = reinterpret_cast<const uint16_t *>(C + (xc + (cy >> 2) * cys + ((cy & 3) << 1)));
                 unsigned long long w = 0;                              // bricks are 32 B = 16 u16 apart
@@ -357,7 +349,7 @@ NAV3D_HD void window_load(const EngineParams &P, const RoomDev &R, const uint8_t
 // Turn one batch into observation floats: clip to [-2, 20], (m + 2) / 22 (:273-275), one float4 per column.
 template <int G>
 NAV3D_HD void window_store(const RoomDev &R, int lane, int x, int y, int z, int a0, const WinBatch<G> &wb, const Rays &r,
-                           int centre_count, const float *lut, float *__restrict__ obs_row, uint16_t *scol) {
+                           int centre_count, const float *lut, float *__restrict__ obs_row) {
     using M = WinMap<G>;
     const uint32_t zbit = 1u << z;
     const int zsh = ((z - 2) & 1) * 8;                   // bit offset of cell z-2 inside the column word
@@ -379,7 +371,6 @@ NAV3D_HD void window_store(const RoomDev &R, int lane, int x, int y, int z, int 
                 // the cells this step's rays see (they may not be in memory yet: marking happens after the gather)
                 if (dyi == 2 && xray) sbits |= centre_col ? r.zmask : zbit;
                 if (dxi == 2 && cy >= r.y0 && cy <= r.y1) sbits |= zbit;
-                if (scol) scol[((cx & 3) << 2) | (cy & 3)] = (uint16_t)sbits;          // what the S tile holds after this step
                 uint32_t c4 = (uint32_t)(wb.cw[a][b] >> zsh);                    // byte k = counter of cell z-2+k
                 if (centre_col) c4 = (c4 & 0xff00ffffu) | ((uint32_t)centre_count << 16);
                 c4 = vminu4_20(c4) + 0x02020202u;                               // clip at 20, +2 = LUT index of a free cell
@@ -479,13 +470,13 @@ NAV3D_HD void mark_seen(const RoomDev &R, uint8_t *envk, int lane, int x, int y,
 template <int G>
 NAV3D_HD void observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z,
                       const Rays &r, int centre_count, bool write_seen, const ObsScalars &sc, const float *lut,
-                      float *__restrict__ obs_row, uint16_t *scol) {
+                      float *__restrict__ obs_row) {
     if (obs_row != nullptr) {
 #pragma unroll
         for (int a0 = 0; a0 < WinMap<G>::NX; a0 += WinMap<G>::AB) {
             WinBatch<G> wb;
-            window_load<G>(P, R, envk, lane, x, y, z, a0, wb, nullptr, false, 0, 0);
-            window_store<G>(R, lane, x, y, z, a0, wb, r, centre_count, lut, obs_row, scol);
+            window_load<G>(P, R, envk, lane, x, y, z, a0, wb);
+            window_store<G>(R, lane, x, y, z, a0, wb, r, centre_count, lut, obs_row);
         }
         write_scalars<G>(P, lane, sc, lut, obs_row);
     }
@@ -518,13 +509,11 @@ NAV3D_HD void reset_env(const EngineParams &P, int env, int lane, int lane_in_wa
     ObsScalars sc;
     sc.facing = 0; sc.last_action = 0; sc.was_near_wall = 0; sc.last_bump = 0; sc.down = r.down;
     sc.visited = 1; sc.total_free = R.n_free;
-    uint16_t *scol = P.scol ? P.scol + (size_t)env * 16 : nullptr;
-    observe<G>(P, R, envk, lane, x, y, z, r, 1, true, sc, lut, obs_row, scol);
+    observe<G>(P, R, envk, lane, x, y, z, r, 1, true, sc, lut, obs_row);
     if (lane == 0) {
         EnvState st;
         st.x = (uint8_t)x; st.y = (uint8_t)y; st.z = (uint8_t)z; st.facing = 0;
-        st.last_action = 0; st.down = (uint8_t)r.down;
-        st.flags = (uint8_t)((r.near_wall ? kNearWall : 0u) | (scol && obs_row ? kSColValid : 0u));
+        st.last_action = 0; st.flags = (uint8_t)(r.near_wall ? kNearWall : 0u); st.down = (uint8_t)r.down;
         st.pad0 = (uint8_t)r.blocked6;
         st.step_count = 0; st.visited_count = 1; st.bump_count = 0; st.ret_centi = 0;
         st.episode = episode_after; st.room = (uint16_t)room_idx; st.pad1 = 0;
@@ -586,10 +575,8 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
     // Issue every load of the step now: first window batch, the counter of the final cell, the three occupancy words.
     // (A caller that wants no observation at all — the inner steps of a fused rollout — skips the window entirely.)
     const bool any_obs = io.obs != nullptr || io.terminal_obs != nullptr;
-    uint16_t *scol = P.scol ? P.scol + (size_t)env * 16 : nullptr;
-    const bool scol_valid = scol != nullptr && (flags & kSColValid) != 0;
     WinBatch<G> wb;
-    if (any_obs) window_load<G>(P, R, envk, lane, x, y, z, 0, wb, scol, scol_valid, st.x, st.y);
+    if (any_obs) window_load<G>(P, R, envk, lane, x, y, z, 0, wb);
     const uint32_t cidx = c_index(R, x, y, z);
     const int c_old = C[cidx];
     const Rays r = cast_rays(P, R, x, y, z);
@@ -613,16 +600,14 @@ NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lan
         ObsScalars sc;
         sc.facing = facing; sc.last_action = st.last_action; sc.was_near_wall = (flags & kWasNearWall) != 0;
         sc.last_bump = (flags & kLastBump) != 0; sc.down = r.down; sc.visited = visited; sc.total_free = R.n_free;
-        window_store<G>(R, lane, x, y, z, 0, wb, r, c_new, lut, orow, scol);
+        window_store<G>(R, lane, x, y, z, 0, wb, r, c_new, lut, orow);
 #pragma unroll
         for (int a0 = WinMap<G>::AB; a0 < WinMap<G>::NX; a0 += WinMap<G>::AB) {
-            window_load<G>(P, R, envk, lane, x, y, z, a0, wb, scol, scol_valid, st.x, st.y);
-            window_store<G>(R, lane, x, y, z, a0, wb, r, c_new, lut, orow, scol);
+            window_load<G>(P, R, envk, lane, x, y, z, a0, wb);
+            window_store<G>(R, lane, x, y, z, a0, wb, r, c_new, lut, orow);
         }
         write_scalars<G>(P, lane, sc, lut, orow);
-        flags |= kSColValid;                       // the streamed S columns now describe the window around (x, y)
-    } else flags &= ~kSColValid;                   // no observation formed: they are stale from here on
-    if (scol == nullptr) flags &= ~kSColValid;
+    }
     // The cells a ray pass marks depend only on the position (L and the room are fixed), and marks are never erased
     // within an episode: every earlier stay at this cell (c_old >= 1, which includes every bump) already marked
     // them.  Only a FIRST visit has anything to write, so revisits skip the ray marking and its scattered traffic.

@@ -373,7 +373,6 @@ struct nav3d_engine {
     unsigned long long *d_occ64 = nullptr;
     uint32_t *d_free = nullptr;
     EnvState *d_states = nullptr;
-    uint16_t *d_scol = nullptr;     // CubicEnv: S words of the window columns, 32 bytes per env (EngineParams::scol)
     uint8_t *d_know = nullptr;
     size_t know_bytes = 0, room_bytes = 0;
     // scratch for rollout / host path
@@ -506,15 +505,6 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     }
     EngineParams &P = e->P;
     P.states = e->d_states;
-    P.scol = nullptr;
-    if (cfg->env_kind == NAV3D_ENV_CUBIC && !getenv("NAV3D_NO_SCOL")) {
-        if ((err = cudaMalloc(&e->d_scol, N * 16 * sizeof(uint16_t))) != cudaSuccess ||
-            (err = cudaMemset(e->d_scol, 0, N * 16 * sizeof(uint16_t))) != cudaSuccess) {
-            nav3d_destroy(e);
-            return fail(NAV3D_ERR_CUDA, std::string("nav3d_create: ") + cudaGetErrorString(err));
-        }
-        P.scol = e->d_scol;
-    }
     P.n_envs = cfg->n_envs;
     P.L = cfg->local_map_length;
     P.env_id0 = cfg->env_id0;
@@ -545,7 +535,7 @@ void nav3d_destroy(nav3d_engine *e) {
     if (!e) return;
     DeviceGuard guard(e->cfg.device);
     free_rooms(e);
-    cudaFree(e->d_states); cudaFree(e->d_scol); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
+    cudaFree(e->d_states); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
     cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_pend_count); cudaFree(e->d_pend_list); cudaFree(e->d_dist_lut);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) {
@@ -670,7 +660,7 @@ int nav3d_lanes_per_env(const nav3d_engine *e) { return e ? e->G : 0; }
 uint64_t nav3d_launch_count(const nav3d_engine *e) { return e ? e->launches : 0; }
 size_t nav3d_device_bytes(const nav3d_engine *e) {
     if (!e) return 0;
-    return e->know_bytes + e->room_bytes + (size_t)e->cfg.n_envs * (sizeof(EnvState) + (e->d_scol ? 32 : 0) + 6);
+    return e->know_bytes + e->room_bytes + (size_t)e->cfg.n_envs * (sizeof(EnvState) + 6);
 }
 
 int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_t *picks, float *obs, void *stream) {
@@ -850,7 +840,7 @@ int nav3d_get_grid(nav3d_engine *e, int32_t env, int16_t *grid, void *stream) {
 
 size_t nav3d_snapshot_bytes(const nav3d_engine *e) {
     if (!e || e->h_rooms.empty()) return 0;
-    return (size_t)e->cfg.n_envs * (sizeof(EnvState) + (e->d_scol ? 32 : 0)) + e->know_bytes;
+    return (size_t)e->cfg.n_envs * sizeof(EnvState) + e->know_bytes;
 }
 
 int nav3d_snapshot(nav3d_engine *e, void *host_buf, size_t bytes) {
@@ -861,8 +851,6 @@ int nav3d_snapshot(nav3d_engine *e, void *host_buf, size_t bytes) {
     const size_t sb = (size_t)e->cfg.n_envs * sizeof(EnvState);
     CUDA_TRY(cudaMemcpy(host_buf, e->d_states, sb, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy((char *)host_buf + sb, e->d_know, e->know_bytes, cudaMemcpyDeviceToHost));
-    if (e->d_scol)
-        CUDA_TRY(cudaMemcpy((char *)host_buf + sb + e->know_bytes, e->d_scol, (size_t)e->cfg.n_envs * 32, cudaMemcpyDeviceToHost));
     return NAV3D_OK;
 }
 
@@ -874,8 +862,6 @@ int nav3d_restore(nav3d_engine *e, const void *host_buf, size_t bytes) {
     const size_t sb = (size_t)e->cfg.n_envs * sizeof(EnvState);
     CUDA_TRY(cudaMemcpy(e->d_states, host_buf, sb, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(e->d_know, (const char *)host_buf + sb, e->know_bytes, cudaMemcpyHostToDevice));
-    if (e->d_scol)
-        CUDA_TRY(cudaMemcpy(e->d_scol, (const char *)host_buf + sb + e->know_bytes, (size_t)e->cfg.n_envs * 32, cudaMemcpyHostToDevice));
     return NAV3D_OK;
 }
 

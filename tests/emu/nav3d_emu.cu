@@ -18,7 +18,6 @@ struct Emu {
     std::vector<unsigned long long> occ64;
     std::vector<uint32_t> free_cells;
     std::vector<EnvState> states;
-    std::vector<uint16_t> scol;
     std::vector<uint8_t> know;
     float lut[nav3d::kLutSize];
     std::vector<float> dist_lut;
@@ -74,8 +73,6 @@ void *emu_create(int n_envs, int L, double crash, unsigned long long seed, unsig
     for (int i = 0; i < 32; i++) e->lut[nav3d::kLutDown + i] = (float)i / (float)L;
     EngineParams &P = e->P;
     P.rooms = e->rooms.data(); P.occz = e->occz.data(); P.occ64 = e->occ64.data(); P.free_cells = e->free_cells.data();
-    e->scol.assign((size_t)n_envs * 16, 0);
-    P.scol = e->simple ? nullptr : e->scol.data();
     P.states = e->states.data(); P.know = e->know.data(); P.env_stride = stride; P.c_off = (uint32_t)c_off;
     P.n_envs = n_envs; P.n_rooms = n_rooms; P.L = L; P.env_id0 = env_id0; P.seed_lo = (uint32_t)seed;
     P.seed_hi = (uint32_t)(seed >> 32); P.auto_reset = auto_reset; P.crash_penalty = crash;
