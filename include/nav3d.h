@@ -139,7 +139,9 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
                uint8_t *terminated, uint8_t *truncated, float *terminal_obs, nav3d_episode *episodes, void *stream);
 
 /* Same step through HOST buffers: the call a CPU-side trainer (SB3's VecEnv.step_wait, Grid_Train.py:228) makes.
- * Copies actions host->device, steps, copies obs/reward/terminated/truncated device->host and waits for them. */
+ * Copies actions host->device, steps, copies obs/reward/terminated/truncated device->host and waits for them.  Large
+ * batches run as a four-chunk pipeline on two internal streams (upload + step of a chunk overlap the download of the
+ * previous one); pinned (page-locked) host buffers are needed for the copies to be asynchronous. */
 int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, uint8_t *terminated,
                     uint8_t *truncated);
 
