@@ -10,8 +10,8 @@ from .spaces import Box, Discrete, cubic_spaces, simple_spaces
 _lib.load()
 
 from .engine import EPISODE_DTYPE, STATE_FIELDS, Engine  # noqa: E402
-from .vec_env import BatchedCubicEnv, BatchedSimpleEnv, StepInfo  # noqa: E402
+from .vec_env import BatchedCubicEnv, BatchedSimpleEnv, NumpyVecEnv, StepInfo  # noqa: E402
 
-__all__ = ["Engine", "BatchedCubicEnv", "BatchedSimpleEnv", "StepInfo", "Room", "Nav3dError", "parse_room_text", "load_room_file",
+__all__ = ["Engine", "BatchedCubicEnv", "BatchedSimpleEnv", "NumpyVecEnv", "StepInfo", "Room", "Nav3dError", "parse_room_text", "load_room_file",
            "load_room_dir", "list_room_files", "default_box_room", "rooms_from_grids", "Discrete", "Box",
            "cubic_spaces", "simple_spaces", "EPISODE_DTYPE", "STATE_FIELDS"]

@@ -148,6 +148,56 @@ class BatchedCubicEnv:
         return info.to_dicts(self._t_start)
 
 
+class NumpyVecEnv:
+    """The numpy face of a batched env, for host-side trainers written against stable-baselines3's ``VecEnv``
+    (``reset() -> np.ndarray``, ``step_async`` / ``step_wait() -> (obs, rewards, dones, infos)`` with SB3's list-of-dicts
+    ``infos``: ``terminal_observation``, ``TimeLimit.truncated`` and Monitor's ``episode`` record).  It wraps
+    ``BatchedCubicEnv`` (or anything with its interface) and costs one device->host copy per step — the contract of the
+    reference's ``SubprocVecEnv`` (``train/Grid_Train.py:170-173``), not the fast path."""
+
+    def __init__(self, env):
+        self.env = env
+        self.num_envs = env.num_envs
+        self.action_space, self.observation_space = env.action_space, env.observation_space
+        self.render_mode = None
+        self._t_start = time.time()
+        self._actions = None
+
+    def reset(self):
+        return self.env.reset().detach().cpu().numpy().copy()
+
+    def step_async(self, actions) -> None:
+        self._actions = np.asarray(actions, dtype=np.int64)
+
+    def step_wait(self):
+        if self._actions is None:
+            raise RuntimeError("step_wait() called without step_async()")
+        obs, rewards, dones, info = self.env.step(torch.as_tensor(self._actions))
+        self._actions = None
+        return (obs.detach().cpu().numpy().copy(), rewards.detach().cpu().numpy().astype(np.float32),
+                dones.detach().cpu().numpy().astype(bool), StepInfo.to_dicts(info, self._t_start))
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self) -> None:
+        self.env.close()
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs
+
+    def get_attr(self, attr_name, indices=None):
+        return self.env.get_attr(attr_name, indices)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        return self.env.env_method(method_name, *args, indices=indices, **kwargs)
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [False] * n
+
+
 class BatchedSimpleEnv:
     """N ``envs/simpleEnv.py::GridAgent`` instances on the GPU (the reference's older env variant; no driver imports it).
 

@@ -396,3 +396,23 @@ def test_batched_vec_env_contract(oracle):
     assert seen_done == 64
     assert venv.get_attr("total_free_cells") == [149] * 64 and len(venv.env_method("get_position")) == 64
     venv.close()
+
+
+def test_numpy_vec_env_adapter_on_gpu():
+    """nav3d.NumpyVecEnv over BatchedCubicEnv: the SubprocVecEnv-shaped numpy interface of a host-side trainer."""
+    from nav3d import BatchedCubicEnv, NumpyVecEnv
+    rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt")]
+    venv = NumpyVecEnv(BatchedCubicEnv(rooms=rooms, num_envs=16, local_map_length=10, seed=2))
+    obs = venv.reset()
+    assert obs.shape == (16, 80) and obs.dtype == np.float32
+    rng = np.random.default_rng(1)
+    ends = 0
+    for t in range(160):
+        obs, rew, dones, infos = venv.step(rng.integers(0, 6, size=16))
+        for i in np.nonzero(dones)[0]:
+            ends += 1
+            assert infos[i]["TimeLimit.truncated"] in (True, False) and infos[i]["episode"]["l"] == 149
+            assert infos[i]["terminal_observation"].shape == (80,) and infos[i]["total_free"] == 149
+    assert ends == 16 and venv.get_attr("total_free_cells") == [149] * 16
+    assert len(venv.env_method("get_position")) == 16
+    venv.close()

@@ -212,3 +212,32 @@ def test_evaluate_policy_and_callback(tmp_path):
     assert (tmp_path / "best" / "best_model.zip").exists()
     z = np.load(tmp_path / "best" / "evaluations.npz")
     assert z["results"].shape == (2, 10) and list(z["timesteps"]) == [48 * 4, 96 * 4]
+
+
+def test_numpy_vec_env_adapter_follows_the_sb3_contract():
+    """nav3d.NumpyVecEnv over a batched env: numpy in/out, SB3-style infos on episode ends."""
+    from nav3d import NumpyVecEnv
+    from nav3d.spaces import cubic_spaces
+    inner = OracleBatchedEnv(tiny_rooms(), 6, seed=3)
+    inner.action_space, inner.observation_space = cubic_spaces()
+    inner.get_attr = lambda name, indices=None: [0] * 6
+    inner.env_method = lambda name, *a, indices=None, **k: [None] * 6
+    venv = NumpyVecEnv(inner)
+    obs = venv.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (6, 80) and obs.dtype == np.float32
+    rng = np.random.default_rng(0)
+    ends = 0
+    for t in range(80):
+        venv.step_async(rng.integers(0, 6, size=6))
+        obs, rew, dones, infos = venv.step_wait()
+        assert obs.shape == (6, 80) and rew.dtype == np.float32 and dones.dtype == bool and len(infos) == 6
+        for i in range(6):
+            if dones[i]:
+                ends += 1
+                assert infos[i]["terminal_observation"].shape == (80,) and "TimeLimit.truncated" in infos[i]
+                assert infos[i]["episode"]["l"] >= 1 and isinstance(infos[i]["episode"]["r"], float)
+            else:
+                assert infos[i] == {}
+    assert ends >= 6                                            # 36- and ~17-step episodes
+    with pytest.raises(RuntimeError):
+        venv.step_wait()
