@@ -4,6 +4,8 @@
 #include "nav3d_core.cuh"
 #include "../../include/nav3d.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -32,14 +34,22 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
     } while (0)
 
 __device__ __forceinline__ void fill_lut(float *lut, int L) {
-    // nav3d_core.cuh kLut*: (m + 2) / 22 for m = -2 .. 20 (CubicEnv.py:273-275), k / 5 (:284), d / L (:287); correctly
-    // rounded f32 quotients like NumPy's
+    // nav3d_core.cuh kLut*: observation value of a knowledge code = (clip(v, -2, 20) + 2) / 22 (CubicEnv.py:273-275),
+    // k / 5 (:284), d / L (:287); correctly rounded f32 quotients like NumPy's
     const int t = threadIdx.x;
-    if (t < 23) lut[t] = __fdiv_rn((float)t, 22.0f);
-    else if (t >= kLutFifth && t < kLutFifth + 6) lut[t] = __fdiv_rn((float)(t - kLutFifth), 5.0f);
+    if (t < 32) {
+        const int v = t == 0 ? -1 : (t == 1 ? -2 : min(t - 2, 20));
+        lut[t] = __fdiv_rn((float)(v + 2), 22.0f);
+    } else if (t >= kLutFifth && t < kLutFifth + 6) lut[t] = __fdiv_rn((float)(t - kLutFifth), 5.0f);
     else if (t >= kLutDown && t < kLutSize) lut[t] = __fdiv_rn((float)(t - kLutDown), (float)L);
     __syncthreads();
 }
+
+// NVTX ranges around the entry points: visible in nsys / ncu --nvtx timelines, no-ops otherwise.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // load_room's grid -> packed room (CubicEnv.py:421-459).  One CTA per room.
@@ -135,36 +145,6 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(EngineParams P, const int
     }
 }
 
-// Pending auto-resets: the step kernel appends finished envs to a list; reset_pending_kernel (next launch on the same
-// stream) resets them.  Keeping the reset (Philox pick, knowledge clear) out of the step kernel keeps its register
-// count low, which is what its occupancy — and so its ability to hide DRAM latency — depends on.
-struct PendingResets {
-    unsigned int *count;        // [0] = entries in list, [1] = CTAs of reset_pending_kernel that have finished
-    int *list;                  // [n_envs]
-};
-
-template <int G, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) step_kernel(EngineParams P, StepIO io, PendingResets pend) {
-    __shared__ float lut[kLutSize];
-    fill_lut(lut, P.L);
-    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (gid / G >= io.env_n) return;
-    const long long env = io.env0 + gid / G;
-    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
-    const int action = (int)io.actions[env];
-    const bool need_reset = step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env) && lane == 0;
-    // warp-aggregated append
-    const unsigned active = __activemask();
-    const unsigned m = __ballot_sync(active, need_reset);
-    if (need_reset) {
-        const int leader = __ffs(m) - 1;
-        unsigned base = 0;
-        if (liw == leader) base = atomicAdd(pend.count, (unsigned)__popc(m));
-        base = __shfl_sync(m, base, leader);
-        pend.list[base + __popc(m & ((1u << liw) - 1u))] = (int)env;
-    }
-}
-
 // Out-of-line reset for the single-launch step kernel: called at the very end of a step, when almost nothing is live, so
 // the kernel's register count stays that of the step itself.
 template <int G>
@@ -187,49 +167,10 @@ __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_co
     const long long env = io.env0 + gid / G;
     const int lane = (int)(gid % G), liw = threadIdx.x & 31;
     const int action = (int)io.actions[env];
-    if (step_env<G, false>(P, io, (int)env, lane, liw, action, lut, env)) {
+    if (step_env<G>(P, io, (int)env, lane, liw, action, lut, env)) {
         const uint32_t episode = P.states[env].episode;       // untouched by a step that ends its episode
         group_sync<G>(liw);                                    // all lanes are done reading the old knowledge
         reset_out_of_line<G>(P, (int)env, lane, liw, episode, lut, io.obs + env * kObsDim);
-    }
-}
-
-// Single-launch variant with the reset inlined: used for small batches, where a second (mostly idle) launch per step
-// costs more than the extra registers.
-template <int G>
-__global__ void __launch_bounds__(kBlock) step_inline_kernel(EngineParams P, StepIO io) {
-    __shared__ float lut[kLutSize];
-    fill_lut(lut, P.L);
-    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (gid / G >= io.env_n) return;
-    const long long env = io.env0 + gid / G;
-    const int lane = (int)(gid % G), liw = threadIdx.x & 31;
-    const int action = (int)io.actions[env];
-    step_env<G, true>(P, io, (int)env, lane, liw, action, lut, env);
-}
-
-template <int G>
-__global__ void __launch_bounds__(kBlock) reset_pending_kernel(EngineParams P, PendingResets pend, float *obs) {
-    __shared__ float lut[kLutSize];
-    __shared__ unsigned n_sh;
-    fill_lut(lut, P.L);
-    if (threadIdx.x == 0) n_sh = *((volatile unsigned int *)pend.count);
-    __syncthreads();
-    const unsigned n = n_sh;
-    const int lane = threadIdx.x % G, liw = threadIdx.x & 31;
-    const unsigned groups_per_block = kBlock / G;
-    for (unsigned i = blockIdx.x * groups_per_block + threadIdx.x / G; i < n; i += gridDim.x * groups_per_block) {
-        const int env = pend.list[i];
-        const uint32_t episode = P.states[env].episode;
-        group_sync<G>(liw);
-        reset_env_philox<G>(P, env, lane, liw, episode, lut, obs + (long long)env * kObsDim);
-    }
-    // the last CTA to finish clears the list for the next step
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned done = atomicAdd(pend.count + 1, 1u);
-        if (done == gridDim.x - 1) { pend.count[0] = 0; pend.count[1] = 0; __threadfence(); }
     }
 }
 
@@ -264,7 +205,7 @@ __global__ void __launch_bounds__(kBlock, 6) rollout_kernel(const __grid_constan
         io.terminal_obs = nullptr; io.episodes = nullptr;
         io.env0 = 0; io.env_n = P.n_envs;
         uint32_t bits = 0;
-        if (step_env<G, false, true>(P, io, (int)env, lane, liw, action, lut, env, &st, &bits)) {
+        if (step_env<G, true>(P, io, (int)env, lane, liw, action, lut, env, &st, &bits)) {
             group_sync<G>(liw);            // all lanes are done reading the old knowledge
             reset_out_of_line<G>(P, (int)env, lane, liw, st.episode, lut, io.obs ? io.obs + env * kObsDim : nullptr);
             group_sync<G>(liw);            // lane 0's record of the new episode is visible
@@ -335,7 +276,7 @@ __global__ void get_state_kernel(EngineParams P, int32_t *out) {
     o[7] = (s.flags & kNearWall) != 0; o[8] = (s.flags & kWasNearWall) != 0; o[9] = (s.flags & kLastBump) != 0;
     o[10] = (s.flags & kDone) != 0; o[11] = s.down; o[12] = s.last_action; o[13] = s.room;
     o[14] = (int32_t)s.episode; o[15] = s.ret_centi;
-    if (P.obs_dim != kObsDim) { o[7] = s.down; o[8] = s.pad0; o[9] = s.pad1; o[11] = 0; }   // simpleEnv: the goal cell
+    if (P.obs_dim != kObsDim) { o[7] = s.down; o[8] = s.blocked6; o[9] = s.own_count; o[11] = 0; }   // simpleEnv: the goal cell
 }
 
 __global__ void get_grid_kernel(EngineParams P, int env, int16_t *out) {
@@ -343,15 +284,26 @@ __global__ void get_grid_kernel(EngineParams P, int env, int16_t *out) {
     const RoomDev R = P.rooms[s.room];
     const int n = R.W * R.D * R.H;
     const uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
-    const uint16_t *S = reinterpret_cast<const uint16_t *>(envk);
-    const uint8_t *C = envk + P.c_off;
+    const uint32_t *K = reinterpret_cast<const uint32_t *>(envk);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int z = i % R.H, y = (i / R.H) % R.D, x = i / (R.H * R.D);
-        const uint32_t sw = S[s_index(R, x, y)], ow = P.occz[R.occz_off + x * R.D + y];
-        int16_t v = -1;
-        if ((sw >> z) & 1u) v = ((ow >> z) & 1u) ? (int16_t)-2 : (int16_t)C[c_index(R, x, y, z)];
+        const int zb = z / 6;
+        const uint32_t code = (K[k_index(R, x, y, zb)] >> (5 * (z - 6 * zb))) & 31u;
+        int16_t v = (int16_t)((int)code - 2);
+        if (code == kCodeUnknown) v = -1;
+        else if (code == kCodeWall) v = -2;
+        else if (code == kCodeOverflow) v = (int16_t)(kOverflowBase + envk[P.ovf_off + ovf_index(R, x, y, z)]);
         out[i] = v;
     }
+}
+
+// Records of envs that were never reset: every move bumps, so stepping such an env by mistake stays inside its block.
+__global__ void init_states_kernel(EnvState *states, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvState s{};
+    s.blocked6 = 0x3f;
+    states[i] = s;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -371,7 +323,7 @@ struct nav3d_engine {
     RoomDev *d_rooms = nullptr;
     uint16_t *d_occz = nullptr;
     unsigned long long *d_occ64 = nullptr;
-    uint32_t *d_free = nullptr;
+    uint32_t *d_free = nullptr, *d_start = nullptr;
     EnvState *d_states = nullptr;
     uint8_t *d_know = nullptr;
     size_t know_bytes = 0, room_bytes = 0;
@@ -379,15 +331,11 @@ struct nav3d_engine {
     float *d_reward = nullptr, *d_obs = nullptr;
     uint8_t *d_term = nullptr, *d_trunc = nullptr;
     long long *d_actions = nullptr;
-    unsigned int *d_pend_count = nullptr;
-    int *d_pend_list = nullptr;
     int minb = 0;               // __launch_bounds__ min CTAs/SM variant of the step kernel (tuning knob)
-    bool inline_reset = false;  // small batches: one launch per step with the reset inlined
-    int reset_mode = 0;         // 0 pending list + second kernel, 1 inlined, 2 out-of-line call in the same kernel
     bool simple = false;        // NAV3D_ENV_SIMPLE
+    bool reset_seen = false;    // a nav3d_reset call has been made since the rooms were loaded
     bool pdl = true;            // programmatic dependent launch of the step kernel (NAV3D_PDL=0 switches it off)
     float *d_dist_lut = nullptr;
-    int reset_grid = 0;
     cudaStream_t own_stream = nullptr;
     static constexpr int kHostChunks = 4;          // nav3d_step_host pipeline depth
     cudaStream_t copy_stream = nullptr;
@@ -415,6 +363,7 @@ struct DeviceGuard {
 
 void free_rooms(nav3d_engine *e) {
     cudaFree(e->d_rooms); cudaFree(e->d_occz); cudaFree(e->d_occ64); cudaFree(e->d_free); cudaFree(e->d_know);
+    cudaFree(e->d_start); e->d_start = nullptr;
     e->d_rooms = nullptr; e->d_occz = nullptr; e->d_occ64 = nullptr; e->d_free = nullptr; e->d_know = nullptr;
     e->know_bytes = 0; e->room_bytes = 0;
     e->h_rooms.clear(); e->h_free.clear(); e->h_nwall.clear();
@@ -440,6 +389,12 @@ unsigned grid_for(long long n_groups, int G) {
 int check_ready(const nav3d_engine *e) {
     if (!e) return fail(NAV3D_ERR_INVALID, "engine is NULL");
     if (e->h_rooms.empty()) return fail(NAV3D_ERR_INVALID, "no rooms loaded: call nav3d_load_rooms first");
+    return NAV3D_OK;
+}
+// the reference raises AttributeError when step() precedes reset() (no self.x yet); here: an error code
+int check_steppable(const nav3d_engine *e) {
+    if (int rc = check_ready(e)) return rc;
+    if (!e->reset_seen) return fail(NAV3D_ERR_INVALID, "envs were not reset since the rooms were loaded: call nav3d_reset first");
     return NAV3D_OK;
 }
 
@@ -475,30 +430,13 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     e->cfg = *cfg;
     e->G = G;
     e->minb = 8;
-    // reset_mode 2 (one launch per step, reset as an out-of-line call) is the default; 0 = pending list + second kernel,
-    // 1 = reset inlined (more registers).  NAV3D_INLINE_RESET selects another mode for experiments and tests.
-    e->inline_reset = true;
-    e->reset_mode = 2;
-    if (const char *ir = getenv("NAV3D_INLINE_RESET")) { e->reset_mode = atoi(ir); e->inline_reset = e->reset_mode != 0; }
     if (const char *mb = getenv("NAV3D_MINB")) e->minb = atoi(mb);
     if (const char *pd = getenv("NAV3D_PDL")) e->pdl = atoi(pd) != 0;
-    // Every global access of the step is a scattered 32-byte sector; the default 64-byte L2 fetch granularity would read
-    // twice the bytes from HBM (measured: profiles/step_kernel_r01_v0_details.csv).  This is a hint; failure is harmless.
-    if (!getenv("NAV3D_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
-        e->reset_grid = sms * 4;
-    }
     const size_t N = (size_t)cfg->n_envs;
     cudaError_t err = cudaSuccess;
     if ((err = cudaMalloc(&e->d_states, N * sizeof(EnvState))) != cudaSuccess ||
-        (err = cudaMemset(e->d_states, 0, N * sizeof(EnvState))) != cudaSuccess ||
         (err = cudaMalloc(&e->d_reward, N * sizeof(float))) != cudaSuccess ||
         (err = cudaMalloc(&e->d_term, N)) != cudaSuccess || (err = cudaMalloc(&e->d_trunc, N)) != cudaSuccess ||
-        (err = cudaMalloc(&e->d_pend_count, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (err = cudaMemset(e->d_pend_count, 0, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (err = cudaMalloc(&e->d_pend_list, N * sizeof(int))) != cudaSuccess ||
         (err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         nav3d_destroy(e);
         return fail(NAV3D_ERR_CUDA, std::string("nav3d_create: ") + cudaGetErrorString(err));
@@ -511,7 +449,7 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     P.seed_lo = (uint32_t)cfg->seed;
     P.seed_hi = (uint32_t)(cfg->seed >> 32);
     P.auto_reset = cfg->auto_reset ? 1 : 0;
-    P.crash_penalty = cfg->crash_penalty;
+    P.rw = reference_reward_params(cfg->crash_penalty);
     e->simple = cfg->env_kind == NAV3D_ENV_SIMPLE;
     P.obs_dim = e->simple ? 6 * cfg->local_map_length + 7 : kObsDim;
     if (e->simple) {
@@ -525,7 +463,6 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
             return fail(NAV3D_ERR_CUDA, std::string("nav3d_create: ") + cudaGetErrorString(err));
         }
         P.dist_lut = e->d_dist_lut;
-        e->inline_reset = true;
     }
     *out = e;
     return NAV3D_OK;
@@ -536,7 +473,7 @@ void nav3d_destroy(nav3d_engine *e) {
     DeviceGuard guard(e->cfg.device);
     free_rooms(e);
     cudaFree(e->d_states); cudaFree(e->d_reward); cudaFree(e->d_term); cudaFree(e->d_trunc);
-    cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_pend_count); cudaFree(e->d_pend_list); cudaFree(e->d_dist_lut);
+    cudaFree(e->d_obs); cudaFree(e->d_actions); cudaFree(e->d_dist_lut);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) {
         cudaStreamDestroy(e->copy_stream);
@@ -552,7 +489,8 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     std::vector<RoomDev> hr((size_t)n_rooms);
     std::vector<uint32_t> dense_off((size_t)n_rooms);
     std::vector<int32_t> wall((size_t)n_rooms);
-    size_t n_dense = 0, n_occz = 0, n_occ64 = 0, n_free_cap = 0, max_s = 0, max_c = 0;
+    size_t n_dense = 0, n_occz = 0, n_occ64 = 0, n_free_cap = 0, max_k = 0, max_cells = 0;
+    std::vector<uint32_t> start((size_t)n_rooms, 0xffffffffu);
     for (int i = 0; i < n_rooms; i++) {
         const nav3d_room_desc &d = rooms[i];
         if (!d.grid) return fail(NAV3D_ERR_INVALID, "room grid is NULL");
@@ -564,7 +502,12 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
                                                    " exceeds the 64x64x16 limit of this build");
         RoomDev &R = hr[(size_t)i];
         R.W = (uint16_t)d.width; R.D = (uint16_t)d.depth; R.H = (uint16_t)d.height;
-        R.ntx = (uint16_t)((d.width + 3) / 4); R.nty = (uint16_t)((d.depth + 3) / 4); R.nbz = (uint16_t)((d.height + 1) / 2);
+        if (e->simple) {       // one u32 per column, 4x4 columns per 64-byte tile
+            R.ntx = (uint16_t)((d.width + 3) / 4); R.nty = (uint16_t)((d.depth + 3) / 4); R.nzb = 1;
+        } else {               // bordered volume: 2 columns below, 1 above (the window reaches x-2 .. x+1); 6 levels per brick
+            R.ntx = (uint16_t)((d.width + kPadLo + 1 + 3) / 4); R.nty = (uint16_t)((d.depth + kPadLo + 1 + 3) / 4);
+            R.nzb = (uint16_t)((d.height + 5) / 6);
+        }
         R.n_free = 0;
         R.occz_off = (uint32_t)n_occz;  n_occz += (size_t)d.width * d.depth;
         R.occx_off = (uint32_t)n_occ64; n_occ64 += (size_t)d.depth * d.height;
@@ -572,8 +515,14 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
         R.free_off = (uint32_t)n_free_cap; n_free_cap += (size_t)d.width * d.depth * d.height;
         dense_off[(size_t)i] = (uint32_t)n_dense; n_dense += (size_t)d.width * d.depth * d.height;
         wall[(size_t)i] = d.wall_code;
-        max_s = std::max(max_s, (size_t)R.ntx * R.nty * 32);
-        max_c = std::max(max_c, (size_t)R.ntx * R.nty * R.nbz * 32);
+        max_k = std::max(max_k, (size_t)(e->simple ? k2_bytes(R) : k_bytes(R)));
+        max_cells = std::max(max_cells, (size_t)d.width * d.depth * d.height);
+        // "Start position=" of the room file (CubicEnv.py:415-416, :461-466): used instead of a random start when it is a
+        // cell of the room and not a wall (the reference re-picks a random one otherwise)
+        if (d.has_start && d.start_x >= 0 && d.start_x < d.width && d.start_y >= 0 && d.start_y < d.depth && d.start_z >= 0 &&
+            d.start_z < d.height &&
+            d.grid[((size_t)d.start_x * d.depth + d.start_y) * d.height + d.start_z] != d.wall_code)
+            start[(size_t)i] = (uint32_t)d.start_x | ((uint32_t)d.start_y << 8) | ((uint32_t)d.start_z << 16);
     }
     std::vector<int8_t> dense(n_dense);
     for (int i = 0; i < n_rooms; i++)
@@ -582,8 +531,9 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
 
     free_rooms(e);
     int8_t *d_dense = nullptr; uint32_t *d_off = nullptr, *d_nwall = nullptr; int32_t *d_wall = nullptr;
-    size_t c_off = align_up(max_s, 128), stride = c_off + align_up(max_c, 128);
-    if (e->simple) { c_off = 0; stride = align_up(2 * max_s, 128); }      // 2 bits per cell: 64-byte tiles
+    // per-env block: [K bricks of the largest room | overflow bytes (one per cell, touched only by counters >= 29)]
+    size_t ovf_off = align_up(max_k, 128), stride = ovf_off + align_up(max_cells, 128);
+    if (e->simple) { ovf_off = 0; stride = align_up(max_k, 128); }
     const size_t know_bytes = stride * (size_t)e->cfg.n_envs;
     auto cleanup_tmp = [&]() { cudaFree(d_dense); cudaFree(d_off); cudaFree(d_nwall); cudaFree(d_wall); };
 #define LOAD_TRY(expr)                                                                                      \
@@ -604,6 +554,8 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     LOAD_TRY(cudaMalloc(&e->d_occ64, sizeof(unsigned long long) * n_occ64));
     LOAD_TRY(cudaMalloc(&e->d_free, sizeof(uint32_t) * n_free_cap));
     LOAD_TRY(cudaMalloc(&e->d_know, know_bytes));
+    LOAD_TRY(cudaMalloc(&e->d_start, sizeof(uint32_t) * n_rooms));
+    LOAD_TRY(cudaMemcpy(e->d_start, start.data(), sizeof(uint32_t) * n_rooms, cudaMemcpyHostToDevice));
     LOAD_TRY(cudaMemcpy(d_dense, dense.data(), n_dense, cudaMemcpyHostToDevice));
     LOAD_TRY(cudaMemcpy(d_off, dense_off.data(), sizeof(uint32_t) * n_rooms, cudaMemcpyHostToDevice));
     LOAD_TRY(cudaMemcpy(d_wall, wall.data(), sizeof(int32_t) * n_rooms, cudaMemcpyHostToDevice));
@@ -617,7 +569,9 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     LOAD_TRY(cudaMemcpy(hr.data(), e->d_rooms, sizeof(RoomDev) * n_rooms, cudaMemcpyDeviceToHost));
     LOAD_TRY(cudaMemcpy(e->h_free.data(), e->d_free, sizeof(uint32_t) * n_free_cap, cudaMemcpyDeviceToHost));
     LOAD_TRY(cudaMemcpy(e->h_nwall.data(), d_nwall, sizeof(uint32_t) * n_rooms, cudaMemcpyDeviceToHost));
-    LOAD_TRY(cudaMemset(e->d_states, 0, sizeof(EnvState) * (size_t)e->cfg.n_envs));
+    init_states_kernel<<<(e->cfg.n_envs + 255) / 256, 256>>>(e->d_states, e->cfg.n_envs);
+    LOAD_TRY(cudaGetLastError());
+    LOAD_TRY(cudaDeviceSynchronize());
 #undef LOAD_TRY
     cleanup_tmp();
     for (int i = 0; i < n_rooms; i++)
@@ -631,7 +585,37 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     e->room_bytes = sizeof(RoomDev) * n_rooms + 2 * n_occz + 8 * n_occ64 + 4 * n_free_cap;
     EngineParams &P = e->P;
     P.rooms = e->d_rooms; P.occz = e->d_occz; P.occ64 = e->d_occ64; P.free_cells = e->d_free;
-    P.know = e->d_know; P.env_stride = stride; P.c_off = (uint32_t)c_off; P.n_rooms = n_rooms;
+    P.know = e->d_know; P.env_stride = stride; P.ovf_off = (uint32_t)ovf_off; P.n_rooms = n_rooms;
+    P.room_start = e->d_start;
+    e->reset_seen = false;
+    return NAV3D_OK;
+}
+
+void nav3d_reward_params_default(nav3d_reward_params *out) {
+    if (!out) return;
+    const RewardParams w = reference_reward_params(-2.0);
+    out->step_cost = w.step_cost; out->revisit_unit = w.revisit_unit; out->revisit_cap = w.revisit_cap;
+    out->crash_penalty = w.crash_penalty; out->near_wall_bonus = w.near_wall_bonus; out->repeat_bonus = w.repeat_bonus;
+    out->reverse_penalty = w.reverse_penalty; out->explore_bonus = w.explore_bonus; out->finish_bonus = w.finish_bonus;
+    out->truncation_penalty = w.truncation_penalty;
+}
+
+int nav3d_set_reward_params(nav3d_engine *e, const nav3d_reward_params *p) {
+    if (!e || !p) return fail(NAV3D_ERR_INVALID, "engine/params is NULL");
+    if (e->simple) return fail(NAV3D_ERR_UNSUPPORTED, "reward parameters apply to NAV3D_ENV_CUBIC only");
+    const double v[10] = {p->step_cost, p->revisit_unit, p->revisit_cap, p->crash_penalty, p->near_wall_bonus, p->repeat_bonus,
+                          p->reverse_penalty, p->explore_bonus, p->finish_bonus, p->truncation_penalty};
+    for (double x : v) if (!std::isfinite(x) || std::fabs(x) > 1e6) return fail(NAV3D_ERR_INVALID, "reward parameter out of range");
+    RewardParams w = reference_reward_params(p->crash_penalty);
+    w.step_cost = p->step_cost; w.revisit_unit = p->revisit_unit; w.revisit_cap = p->revisit_cap;
+    w.near_wall_bonus = p->near_wall_bonus; w.repeat_bonus = p->repeat_bonus; w.reverse_penalty = p->reverse_penalty;
+    w.explore_bonus = p->explore_bonus; w.finish_bonus = p->finish_bonus; w.truncation_penalty = p->truncation_penalty;
+    w.c_step = reward_centi(w.step_cost); w.c_revisit_unit = reward_centi(w.revisit_unit);
+    w.c_revisit_cap = reward_centi(w.revisit_cap); w.c_near_wall = reward_centi(w.near_wall_bonus);
+    w.c_repeat = reward_centi(w.repeat_bonus); w.c_reverse = reward_centi(w.reverse_penalty);
+    w.c_explore = reward_centi(w.explore_bonus); w.c_finish = reward_centi(w.finish_bonus);
+    w.c_trunc = reward_centi(w.truncation_penalty);
+    e->P.rw = w;
     return NAV3D_OK;
 }
 
@@ -669,6 +653,8 @@ int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_
     if (n == 0) return NAV3D_OK;
     if (obs && !e->simple && ((uintptr_t)obs & 15u)) return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
     NAV3D_DEVICE(e);
+    NvtxRange range("nav3d_reset");
+    e->reset_seen = true;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
@@ -689,7 +675,6 @@ namespace {
 // Launch the step of envs [env0, env0 + n) on `s` (the whole engine: env0 = 0, n = n_envs).
 int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
     io.env0 = env0; io.env_n = n;
-    PendingResets pend{e->d_pend_count, e->d_pend_list};
     const int minb = e->minb;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
@@ -705,33 +690,16 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
             else cudaLaunchKernelEx(&cfg, simple_step_kernel<G, 8>, e->P, io);
             return NAV3D_OK;
         }
-        if (e->inline_reset) {
-            if (e->reset_mode == 2) {
-                switch (minb) {
-                    case 6: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 6>, e->P, io); break;
-                    case 10: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 10>, e->P, io); break;
-                    default: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 8>, e->P, io); break;
-                }
-            } else step_inline_kernel<G><<<grid, kBlock, 0, s>>>(e->P, io);
-            return NAV3D_OK;
-        }
         switch (minb) {
-            case 4: step_kernel<G, 4><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
-            case 6: step_kernel<G, 6><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
-            case 8: step_kernel<G, 8><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
-            case 10: step_kernel<G, 10><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
-            case 12: step_kernel<G, 12><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
-            case 16: step_kernel<G, 16><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
-            default: step_kernel<G, 1><<<grid, kBlock, 0, s>>>(e->P, io, pend); break;
-        }
-        if (e->P.auto_reset) {
-            unsigned rgrid = (unsigned)std::min<long long>(e->reset_grid, ((long long)n * G + kBlock - 1) / kBlock);
-            reset_pending_kernel<G><<<rgrid, kBlock, 0, s>>>(e->P, pend, io.obs);
+            case 6: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 6>, e->P, io); break;
+            case 10: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 10>, e->P, io); break;
+            case 12: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 12>, e->P, io); break;
+            default: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 8>, e->P, io); break;
         }
         return NAV3D_OK;
     });
     if (rc) return rc;
-    e->launches += (e->P.auto_reset && !e->inline_reset) ? 2 : 1;
+    e->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return NAV3D_OK;
 }
@@ -742,12 +710,13 @@ extern "C" {
 
 int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, double *reward64,
                uint8_t *terminated, uint8_t *truncated, float *terminal_obs, nav3d_episode *episodes, void *stream) {
-    if (int rc = check_ready(e)) return rc;
+    if (int rc = check_steppable(e)) return rc;
     if (!actions || !obs || !reward || !terminated || !truncated)
         return fail(NAV3D_ERR_INVALID, "actions, obs, reward, terminated and truncated are required");
     if (!e->simple && (((uintptr_t)obs & 15u) || (terminal_obs && ((uintptr_t)terminal_obs & 15u))))
         return fail(NAV3D_ERR_INVALID, "obs / terminal_obs must be 16-byte aligned");
     NAV3D_DEVICE(e);
+    NvtxRange range("nav3d_step");
     StepIO io;
     io.actions = reinterpret_cast<const long long *>(actions);
     io.obs = obs; io.reward = reward; io.reward64 = reward64; io.terminated = terminated; io.truncated = truncated;
@@ -760,9 +729,10 @@ int nav3d_step(nav3d_engine *e, const int64_t *actions, float *obs, float *rewar
 // the observations (320 B per env) is what bounds this path (PCIe), so everything else hides behind it.
 int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *reward, uint8_t *terminated,
                     uint8_t *truncated) {
-    if (int rc = check_ready(e)) return rc;
+    if (int rc = check_steppable(e)) return rc;
     if (!actions || !obs || !reward || !terminated || !truncated) return fail(NAV3D_ERR_INVALID, "NULL host buffer");
     NAV3D_DEVICE(e);
+    NvtxRange range("nav3d_step_host");
     const size_t N = (size_t)e->cfg.n_envs;
     const size_t obs_dim = (size_t)e->P.obs_dim;
     if (!e->d_obs) CUDA_TRY(cudaMalloc(&e->d_obs, N * obs_dim * sizeof(float)));
@@ -772,8 +742,7 @@ int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *
         for (auto &ev : e->chunk_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     cudaStream_t sc = e->own_stream, sd = e->copy_stream;
-    // pending-list resets (mode 0) share one list per engine: keep that variant in one piece
-    const int chunks = (N >= 65536 && (e->inline_reset || e->simple)) ? nav3d_engine::kHostChunks : 1;
+    const int chunks = N >= 65536 ? nav3d_engine::kHostChunks : 1;
     StepIO io;
     io.actions = e->d_actions; io.obs = e->d_obs; io.reward = e->d_reward; io.reward64 = nullptr;
     io.terminated = e->d_term; io.truncated = e->d_trunc; io.terminal_obs = nullptr; io.episodes = nullptr;
@@ -795,7 +764,7 @@ int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *
 
 int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, float *obs_last, float *reward,
                          uint8_t *done, uint8_t *actions_out, void *stream) {
-    if (int rc = check_ready(e)) return rc;
+    if (int rc = check_steppable(e)) return rc;
     if (T < 0) return fail(NAV3D_ERR_INVALID, "T must be >= 0");
 
     if (e->simple) return fail(NAV3D_ERR_UNSUPPORTED, "nav3d_rollout_random is implemented for NAV3D_ENV_CUBIC only");
@@ -804,6 +773,7 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
     if ((obs && ((uintptr_t)obs & 15u)) || (obs_last && ((uintptr_t)obs_last & 15u)))
         return fail(NAV3D_ERR_INVALID, "obs must be 16-byte aligned");
     NAV3D_DEVICE(e);
+    NvtxRange range("nav3d_rollout_random");
     cudaStream_t s = (cudaStream_t)stream;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
@@ -862,6 +832,7 @@ int nav3d_restore(nav3d_engine *e, const void *host_buf, size_t bytes) {
     const size_t sb = (size_t)e->cfg.n_envs * sizeof(EnvState);
     CUDA_TRY(cudaMemcpy(e->d_states, host_buf, sb, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(e->d_know, (const char *)host_buf + sb, e->know_bytes, cudaMemcpyHostToDevice));
+    e->reset_seen = true;
     return NAV3D_OK;
 }
 

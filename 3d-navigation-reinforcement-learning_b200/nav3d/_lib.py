@@ -12,7 +12,7 @@ PKG_ROOT = Path(__file__).resolve().parent.parent          # 3d-navigation-reinf
 REPO_ROOT = PKG_ROOT.parent
 LIB_PATH = PKG_ROOT / "lib" / "libnav3d_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OBS_DIM = 80
 STATE_INTS = 16
 ENV_CUBIC, ENV_SIMPLE = 0, 1
@@ -37,7 +37,15 @@ class Config(C.Structure):
 
 class RoomDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("depth", C.c_int32), ("height", C.c_int32), ("wall_code", C.c_int32),
-                ("grid", C.c_void_p)]
+                ("grid", C.c_void_p), ("has_start", C.c_int32), ("start_x", C.c_int32), ("start_y", C.c_int32),
+                ("start_z", C.c_int32)]
+
+
+class RewardParams(C.Structure):
+    """``nav3d_reward_params``: the literals of ``compute_reward`` (reference ``envs/CubicEnv.py:169-224``)."""
+    _fields_ = [(n, C.c_double) for n in ("step_cost", "revisit_unit", "revisit_cap", "crash_penalty", "near_wall_bonus",
+                                          "repeat_bonus", "reverse_penalty", "explore_bonus", "finish_bonus",
+                                          "truncation_penalty")]
 
 
 # every symbol include/nav3d.h declares: (restype, argtypes)
@@ -47,6 +55,8 @@ SYMBOLS = {
     "nav3d_abi_version": (C.c_int, []),
     "nav3d_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "nav3d_destroy": (None, [_P]),
+    "nav3d_reward_params_default": (None, [C.POINTER(RewardParams)]),
+    "nav3d_set_reward_params": (C.c_int, [_P, C.POINTER(RewardParams)]),
     "nav3d_load_rooms": (C.c_int, [_P, C.c_int32, C.POINTER(RoomDesc)]),
     "nav3d_room_info": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     "nav3d_room_free_cell": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),

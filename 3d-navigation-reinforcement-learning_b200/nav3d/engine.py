@@ -46,6 +46,7 @@ class Engine:
             check(self._lib.nav3d_create(C.byref(cfg), C.byref(self._h)))
         self.n_envs = int(n_envs)
         self.local_map_length = int(local_map_length)
+        self.crash_penalty = float(crash_penalty)
         self.auto_reset = bool(auto_reset)
         self.seed = int(seed)
         self.env_id0 = int(env_id0)
@@ -67,7 +68,10 @@ class Engine:
             g = np.ascontiguousarray(r.grid, dtype=np.int8)
             keep.append(g)
             w, d, h = g.shape
-            descs[i] = RoomDesc(width=w, depth=d, height=h, wall_code=int(r.wall_code), grid=g.ctypes.data)
+            st = getattr(r, "start", None)
+            descs[i] = RoomDesc(width=w, depth=d, height=h, wall_code=int(r.wall_code), grid=g.ctypes.data,
+                                has_start=int(st is not None), start_x=int(st[0]) if st else 0,
+                                start_y=int(st[1]) if st else 0, start_z=int(st[2]) if st else 0)
         check(self._lib.nav3d_load_rooms(self._h, len(rooms), descs))
         self.rooms = rooms
         info = (C.c_int32 * 6)()
@@ -77,6 +81,19 @@ class Engine:
             self.room_dims.append((info[0], info[1], info[2]))
             self.room_free.append(int(info[3]))
             self.room_walls.append(int(info[4]))
+
+    def set_reward_params(self, **kwargs):
+        """Override literals of ``compute_reward`` (reference ``envs/CubicEnv.py:169-224``); names are the fields of
+        ``nav3d_reward_params``.  Unnamed ones keep their current reference default."""
+        p = _lib.RewardParams()
+        self._lib.nav3d_reward_params_default(C.byref(p))
+        p.crash_penalty = self.crash_penalty
+        for k, v in kwargs.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown reward parameter {k!r}")
+            setattr(p, k, float(v))
+        check(self._lib.nav3d_set_reward_params(self._h, C.byref(p)))
+        self.crash_penalty = float(p.crash_penalty)
 
     def free_cell(self, room: int, k: int):
         xyz = (C.c_int32 * 3)()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NAV3D_ABI_VERSION 1
+#define NAV3D_ABI_VERSION 2
 #define NAV3D_OBS_DIM 80          /* envs/CubicEnv.py:58-62 */
 #define NAV3D_NUM_ACTIONS 6       /* envs/CubicEnv.py:56   */
 #define NAV3D_STATE_INTS 16       /* ints per env written by nav3d_get_state */
@@ -83,7 +83,31 @@ typedef struct {
     int32_t width, depth, height;
     int32_t wall_code;
     const int8_t *grid;           /* HOST, width*depth*height bytes */
+    int32_t has_start;            /* 1: the room file has a "Start position=" line (envs/CubicEnv.py:415-416) */
+    int32_t start_x, start_y, start_z;   /* used for every reset into this room unless it is a wall or outside the room,
+                                          * in which case a random free cell is drawn as the reference does (:461-466) */
 } nav3d_room_desc;
+
+/* The literals of compute_reward (envs/CubicEnv.py:169-224) as a POD; nav3d_reward_params_default fills in the
+ * reference's values, which is what an engine uses until nav3d_set_reward_params is called (CubicEnv only).
+ *   reward = step_cost - min(visit_count * revisit_unit, revisit_cap)
+ *            + (bumped ? crash_penalty : [was_near_wall] near_wall_bonus + [same horizontal action again] repeat_bonus
+ *                                        - [backwards twice] reverse_penalty)
+ *            + [first visit] explore_bonus + [>= 84 % explored] finish_bonus + [step limit] truncation_penalty
+ * nav3d_episode.episode_return is accumulated in 1/100 units: exact when every constant except crash_penalty is a
+ * multiple of 0.01 (true for the reference's), rounded per term otherwise. */
+typedef struct {
+    double step_cost;             /* -0.05  :175 */
+    double revisit_unit;          /*  0.02  :179 */
+    double revisit_cap;           /*  0.5   :180 */
+    double crash_penalty;         /* -2.0   :28, :187 (same value as nav3d_config.crash_penalty) */
+    double near_wall_bonus;       /*  0.15  :193 */
+    double repeat_bonus;          /*  0.05  :199 */
+    double reverse_penalty;       /*  0.5   :203 (subtracted) */
+    double explore_bonus;         /*  1.0   :209 */
+    double finish_bonus;          /* 100.0  :215 */
+    double truncation_penalty;    /* -5.0   :221 */
+} nav3d_reward_params;
 
 /* Written by nav3d_step only for envs whose episode ended in that step (Monitor's info["episode"] plus the
  * attributes train/evaluate_grid.py:216-218 reads). 32 bytes. */
@@ -105,10 +129,16 @@ int nav3d_abi_version(void);
 int nav3d_create(const nav3d_config *cfg, nav3d_engine **out);
 void nav3d_destroy(nav3d_engine *e);
 
+void nav3d_reward_params_default(nav3d_reward_params *out);
+/* Takes effect from the next step on; may be called at any time (host-side copy, no device work). */
+int nav3d_set_reward_params(nav3d_engine *e, const nav3d_reward_params *params);
+
 /* The room table: replaces the per-reset text parse + free-cell scan of load_room (envs/CubicEnv.py:402-459).
  * Dense grids are uploaded once; a CUDA kernel packs each room into bit-packed occupancy words (three orientations)
  * and builds the ordered free-cell list; per-env knowledge storage is sized for the largest room.
- * After this call every env must be reset before it is stepped. */
+ * After this call the envs must be reset before they are stepped: nav3d_step / nav3d_step_host / nav3d_rollout_random
+ * fail with NAV3D_ERR_INVALID until nav3d_reset has been called (the reference raises AttributeError for step-before-
+ * reset); an env that a partial reset left out only bumps in place until it is reset. */
 int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *rooms);
 /* out6 = width, depth, height, total_free_cells (= max_steps, CubicEnv.py:459), n_wall_cells, reserved.  Synchronises. */
 int nav3d_room_info(nav3d_engine *e, int32_t room, int32_t *out6);
@@ -121,8 +151,9 @@ int nav3d_lanes_per_env(const nav3d_engine *e);
 /* GridAgent.reset (envs/CubicEnv.py:77-108) for a set of envs.
  *   env_ids : DEVICE int32[n] or NULL = envs 0..n-1 (then n must be <= n_envs)
  *   picks   : DEVICE int32[n][2] = (room index, k-th free cell) per listed env — the two random.choice draws of
- *             load_room (:407, :462; for simpleEnv a third column would be the goal: see nav3d_reset_simple) —
- *             or NULL = draw them from the env's Philox reset stream
+ *             load_room (:407, :462) — for a NAV3D_ENV_SIMPLE engine int32[n][3]: the third column is the index of the goal in the
+ *             same free-cell list (envs/simpleEnv.py:419-426) — or NULL = draw them from the env's Philox reset stream.
+ *             A room with a usable "Start position" starts there whatever k says.
  *   obs     : DEVICE f32[n_envs][obs_dim]; rows of the listed envs are written; may be NULL */
 int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_t *picks, float *obs, void *stream);
 
@@ -161,7 +192,7 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
  *    excluding crash penalties */
 int nav3d_get_state(nav3d_engine *e, int32_t *state, void *stream);
 /* self.internal_grid of one env (CubicEnv.py:84-85) rebuilt from the packed representation, DEVICE int16
- * [width][depth][height] of the env's current room (C order).  Visit counters saturate at 255. */
+ * [width][depth][height] of the env's current room (C order).   Visit counters saturate at 255. */
 int nav3d_get_grid(nav3d_engine *e, int32_t env, int16_t *grid, void *stream);
 
 /* Checkpoint / restore of the complete mutable engine state (scalars + knowledge grids), HOST buffers. */

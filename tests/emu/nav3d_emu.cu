@@ -1,7 +1,8 @@
-// nav3d_emu.cu — DEBUGGING AID, tests only.  Compiles the device logic of csrc/nav3d_core.cuh for the HOST with one lane
-// per env (G = 1) so that the packed-representation logic can be checked against the oracle in the GPU-less build
-// container.  It is not linked into libnav3d_b200.so and nothing in the product imports it; it says nothing about the
-// concurrency of the real kernels, which only the -m gpu tests exercise.
+// nav3d_emu.cu — DEBUGGING AID, tests only.  Compiles the device logic of csrc/nav3d_core.cuh for the HOST so that the
+// packed-representation logic can be checked against the oracle in the GPU-less build container.  The G lanes of an env's
+// group run one after the other (ascending or descending lane order), the group's OR-reduction happens between the two
+// halves of a step.  It is not linked into libnav3d_b200.so and nothing in the product imports it; it says little about
+// the concurrency of the real kernels, which only the -m gpu tests exercise.
 #include "../../3d-navigation-reinforcement-learning_b200/csrc/nav3d_core.cuh"
 
 #include <cmath>
@@ -22,20 +23,64 @@ struct Emu {
     float lut[nav3d::kLutSize];
     std::vector<float> dist_lut;
     bool simple = false;
+    int G = 1;
+    bool descending = false;
 };
+
+template <int G> static void reset_one(Emu *e, int env, uint32_t room, uint32_t k, uint32_t ep_after, float *orow) {
+    ResetCtx c;
+    uint32_t nbr = 0;
+    for (int lane = 0; lane < G; lane++) reset_clear<G>(e->P, env, lane, room);
+    for (int i = 0; i < G; i++) {
+        const int lane = e->descending ? G - 1 - i : i;
+        ResetCtx ci;
+        nbr |= reset_lane<G>(e->P, env, lane, room, k, ep_after, e->lut, orow, ci);
+        c = ci;
+    }
+    reset_commit(e->P, env, 0, c, nbr);
+}
+template <int G> static void reset_one_philox(Emu *e, int env, uint32_t episode, float *orow) {
+    uint32_t room, k;
+    reset_picks(e->P, env, episode, room, k);
+    reset_one<G>(e, env, room, k, episode + 1u, orow);
+}
+template <int G> static void step_all(Emu *e, const StepIO &io, const long long *actions) {
+    for (int env = 0; env < e->P.n_envs; env++) {
+        StepCtx c;
+        uint32_t nbr = 0;
+        for (int i = 0; i < G; i++) {
+            const int lane = e->descending ? G - 1 - i : i;
+            StepCtx ci;
+            nbr |= step_lane<G>(e->P, io, env, lane, (int)actions[env], e->lut, env, nullptr, ci);
+            c = ci;
+        }
+        step_commit<G>(e->P, io, env, 0, c, nbr, env, nullptr, nullptr);
+        if (c.will_reset) reset_one_philox<G>(e, env, e->states[env].episode, io.obs + (size_t)env * kObsDim);
+    }
+}
+#define EMU_DISPATCH(G_, CALL)                                                                   \
+    switch (G_) {                                                                                \
+        case 1: { constexpr int G = 1; CALL; } break;   case 2: { constexpr int G = 2; CALL; } break;   \
+        case 4: { constexpr int G = 4; CALL; } break;   case 8: { constexpr int G = 8; CALL; } break;   \
+        case 16: { constexpr int G = 16; CALL; } break; default: { constexpr int G = 32; CALL; } break; \
+    }
 
 extern "C" {
 
 void *emu_create(int n_envs, int L, double crash, unsigned long long seed, unsigned env_id0, int auto_reset, int n_rooms,
-                 const int *dims, const int8_t *dense, const unsigned *dense_off, int wall_code, int simple, double cell_size) {
+                 const int *dims, const int8_t *dense, const unsigned *dense_off, int wall_code, int simple, double cell_size,
+                 int lanes, int descending) {
     Emu *e = new Emu();
     e->simple = simple != 0;
-    size_t max_s = 0, max_c = 0;
+    e->G = lanes; e->descending = descending != 0;
+    size_t max_k = 0, max_cells = 0;
     for (int r = 0; r < n_rooms; r++) {
         const int W = dims[3 * r], D = dims[3 * r + 1], H = dims[3 * r + 2];
         const int8_t *g = dense + dense_off[r];
         RoomDev R{};
-        R.W = W; R.D = D; R.H = H; R.ntx = (W + 3) / 4; R.nty = (D + 3) / 4; R.nbz = (H + 1) / 2;
+        R.W = W; R.D = D; R.H = H;
+        if (e->simple) { R.ntx = (W + 3) / 4; R.nty = (D + 3) / 4; R.nzb = 1; }
+        else { R.ntx = (W + 3 + 3) / 4; R.nty = (D + 3 + 3) / 4; R.nzb = (H + 5) / 6; }
         R.occz_off = (uint32_t)e->occz.size();
         for (int x = 0; x < W; x++) for (int y = 0; y < D; y++) {
             uint16_t b = 0;
@@ -60,22 +105,26 @@ void *emu_create(int n_envs, int L, double crash, unsigned long long seed, unsig
             if (g[(x * D + y) * H + z] != wall_code) { e->free_cells.push_back(x | (y << 8) | (z << 16)); nf++; }
         R.n_free = nf;
         e->rooms.push_back(R);
-        max_s = std::max(max_s, (size_t)R.ntx * R.nty * 32);
-        max_c = std::max(max_c, (size_t)R.ntx * R.nty * R.nbz * 32);
+        max_k = std::max(max_k, (size_t)(e->simple ? k2_bytes(R) : k_bytes(R)));
+        max_cells = std::max(max_cells, (size_t)W * D * H);
     }
-    size_t c_off = (max_s + 127) / 128 * 128, stride = c_off + (max_c + 127) / 128 * 128;
-    if (e->simple) { c_off = 0; stride = (2 * max_s + 127) / 128 * 128; }
+    size_t ovf_off = (max_k + 127) / 128 * 128, stride = ovf_off + (max_cells + 127) / 128 * 128;
+    if (e->simple) { ovf_off = 0; stride = (max_k + 127) / 128 * 128; }
     for (int c = 0; c <= L; c++) e->dist_lut.push_back((float)(std::nearbyint((double)c * cell_size * 100.0) / 100.0));
     e->states.assign((size_t)n_envs, EnvState{});
     e->know.assign(stride * (size_t)n_envs, 0xAB);     // poison: a reset must clear what it uses
-    for (int i = 0; i < 23; i++) e->lut[i] = (float)i / 22.0f;
+    for (int i = 0; i < kLutSize; i++) e->lut[i] = 0.f;
+    for (int i = 0; i < 32; i++) {
+        const int v = i == 0 ? -1 : (i == 1 ? -2 : std::min(i - 2, 20));
+        e->lut[i] = (float)(v + 2) / 22.0f;
+    }
     for (int i = 0; i < 6; i++) e->lut[nav3d::kLutFifth + i] = (float)i / 5.0f;
     for (int i = 0; i < 32; i++) e->lut[nav3d::kLutDown + i] = (float)i / (float)L;
     EngineParams &P = e->P;
     P.rooms = e->rooms.data(); P.occz = e->occz.data(); P.occ64 = e->occ64.data(); P.free_cells = e->free_cells.data();
-    P.states = e->states.data(); P.know = e->know.data(); P.env_stride = stride; P.c_off = (uint32_t)c_off;
+    P.states = e->states.data(); P.know = e->know.data(); P.env_stride = stride; P.ovf_off = (uint32_t)ovf_off;
     P.n_envs = n_envs; P.n_rooms = n_rooms; P.L = L; P.env_id0 = env_id0; P.seed_lo = (uint32_t)seed;
-    P.seed_hi = (uint32_t)(seed >> 32); P.auto_reset = auto_reset; P.crash_penalty = crash;
+    P.seed_hi = (uint32_t)(seed >> 32); P.auto_reset = auto_reset; P.rw = reference_reward_params(crash);
     P.dist_lut = e->dist_lut.data(); P.obs_dim = e->simple ? 6 * L + 7 : kObsDim;
     return e;
 }
@@ -93,8 +142,8 @@ void emu_reset(void *h, const int *env_ids, int n, const int *picks, float *obs)
             else simple_reset_env_philox<1>(e->P, env, 0, 0, ep, orow);
             continue;
         }
-        if (picks) reset_env<1>(e->P, env, 0, 0, (uint32_t)picks[2 * i], (uint32_t)picks[2 * i + 1], ep + 1, e->lut, orow);
-        else reset_env_philox<1>(e->P, env, 0, 0, ep, e->lut, orow);
+        if (picks) { EMU_DISPATCH(e->G, reset_one<G>(e, env, (uint32_t)picks[2 * i], (uint32_t)picks[2 * i + 1], ep + 1, orow)) }
+        else { EMU_DISPATCH(e->G, reset_one_philox<G>(e, env, ep, orow)) }
     }
 }
 void emu_step(void *h, const long long *actions, float *obs, float *reward, double *reward64, uint8_t *term,
@@ -107,7 +156,7 @@ void emu_step(void *h, const long long *actions, float *obs, float *reward, doub
         for (int env = 0; env < e->P.n_envs; env++) simple_step_env<1>(e->P, io, env, 0, 0, (int)actions[env], env);
         return;
     }
-    for (int env = 0; env < e->P.n_envs; env++) step_env<1, true>(e->P, io, env, 0, 0, (int)actions[env], e->lut, env);
+    EMU_DISPATCH(e->G, step_all<G>(e, io, actions))
 }
 void emu_get_state(void *h, int *out) {
     Emu *e = (Emu *)h;
@@ -118,7 +167,7 @@ void emu_get_state(void *h, int *out) {
         o[6] = s.step_count; o[7] = (s.flags & kNearWall) != 0; o[8] = (s.flags & kWasNearWall) != 0;
         o[9] = (s.flags & kLastBump) != 0; o[10] = (s.flags & kDone) != 0; o[11] = s.down; o[12] = s.last_action;
         o[13] = s.room; o[14] = s.episode; o[15] = s.ret_centi;
-        if (e->simple) { o[7] = s.down; o[8] = s.pad0; o[9] = s.pad1; o[11] = 0; }
+        if (e->simple) { o[7] = s.down; o[8] = s.blocked6; o[9] = s.own_count; o[11] = 0; }
     }
 }
 void emu_get_grid(void *h, int env, int16_t *out) {
@@ -126,18 +175,18 @@ void emu_get_grid(void *h, int env, int16_t *out) {
     const EnvState s = e->states[env];
     const RoomDev R = e->rooms[s.room];
     const uint8_t *envk = e->know.data() + (size_t)env * e->P.env_stride;
-    const uint16_t *S = (const uint16_t *)envk;
-    const uint8_t *C = envk + e->P.c_off;
+    const uint32_t *K = (const uint32_t *)envk;
     if (e->simple) {
-        const uint32_t *K = (const uint32_t *)envk;
         for (int x = 0; x < R.W; x++) for (int y = 0; y < R.D; y++) for (int z = 0; z < R.H; z++)
             out[(x * R.D + y) * R.H + z] = (int16_t)(k2_code(K[s_index(R, x, y)], z) - 1);
         return;
     }
     for (int x = 0; x < R.W; x++) for (int y = 0; y < R.D; y++) for (int z = 0; z < R.H; z++) {
-        const uint32_t sw = S[s_index(R, x, y)], ow = e->occz[R.occz_off + x * R.D + y];
-        int16_t v = -1;
-        if ((sw >> z) & 1u) v = ((ow >> z) & 1u) ? -2 : (int16_t)C[c_index(R, x, y, z)];
+        const uint32_t code = (K[k_index(R, x, y, z / 6)] >> (5 * (z % 6))) & 31u;
+        int16_t v = (int16_t)code - 2;
+        if (code == kCodeUnknown) v = -1;
+        else if (code == kCodeWall) v = -2;
+        else if (code == kCodeOverflow) v = (int16_t)(kOverflowBase + envk[e->P.ovf_off + ovf_index(R, x, y, z)]);
         out[(x * R.D + y) * R.H + z] = v;
     }
 }

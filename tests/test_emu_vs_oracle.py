@@ -12,11 +12,12 @@ from nav3d.rooms import load_room_dir, load_room_file
 pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc needed to build the host emulation")
 
 
-def run_lockstep(oracle, rooms, n, L, steps, seed, auto_reset=True, crash=-2.0, check_state_every=1):
+def run_lockstep(oracle, rooms, n, L, steps, seed, auto_reset=True, crash=-2.0, check_state_every=1, lanes=1,
+                 descending=False):
     from emu_harness import EmuEngine
     orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
     ov = oracle.OracleVec(n, orooms, L, crash, seed, 0, auto_reset)
-    em = EmuEngine(n, rooms, L, crash, seed, 0, auto_reset)
+    em = EmuEngine(n, rooms, L, crash, seed, 0, auto_reset, lanes=lanes, descending=descending)
     for i, r in enumerate(orooms):
         assert em.n_free(i) == r.n_free
     o0 = ov.reset()
@@ -46,6 +47,20 @@ def test_emu_heterogeneous_rooms(oracle):
     rooms = load_room_dir(ROOMS / "P3_training", sort=True) + [load_room_file(ROOMS / "P2_training" / "tightcorridor.txt")]
     n_done = run_lockstep(oracle, rooms, n=72, L=10, steps=700, seed=11, check_state_every=7)
     assert n_done > 0          # maze_3d_tunnels (149 free) and tightcorridor (302) truncate early
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
+@pytest.mark.parametrize("descending", [False, True])
+def test_emu_lane_groups(oracle, lanes, descending):
+    """The G lanes of a group run one after the other, in either order: no lane may depend on what a sibling wrote in the
+    same step (readers of a word another lane marks re-derive the marks themselves)."""
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)[:3] + [load_room_file(ROOMS / "P3_training" / "maze_7x7_seed22.txt"),
+                                                                    load_room_file(ROOMS / "P3_training" / "kitchen2.txt")]
+    n_done = run_lockstep(oracle, rooms, n=24, L=10, steps=1100, seed=lanes, lanes=lanes, descending=descending,
+                          check_state_every=3)
+    assert n_done > 0
+    from edge_rooms import degenerate_rooms, max_size_rooms
+    run_lockstep(oracle, max_size_rooms() + degenerate_rooms(), n=16, L=15, steps=300, seed=9, lanes=lanes, descending=descending)
 
 
 @pytest.mark.parametrize("L", [1, 4, 15, 40])

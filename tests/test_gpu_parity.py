@@ -236,16 +236,64 @@ def test_config3_full_size_sample_against_oracle(oracle):
     assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
 
 
-@pytest.mark.parametrize("inline,minb", [("0", "8"), ("0", "12"), ("1", "8"), ("2", "8"), ("2", "10")])
-def test_both_reset_paths_and_occupancy_variants(oracle, monkeypatch, inline, minb):
-    """Auto-reset has three implementations — out-of-line call in the step kernel (default, mode 2), inlined (1), pending
-    list + second kernel (0); all of them, and the register-capped kernel variants, must give the same bits."""
-    monkeypatch.setenv("NAV3D_INLINE_RESET", inline)
+@pytest.mark.parametrize("minb", ["6", "8", "10", "12"])
+def test_occupancy_variants(oracle, monkeypatch, minb):
+    """The register-capped instantiations of the step kernel (__launch_bounds__ min CTAs per SM, NAV3D_MINB) must give the
+    same bits, auto-reset (an out-of-line device call at the end of the step) included."""
     monkeypatch.setenv("NAV3D_MINB", minb)
     rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt"), load_room_file(ROOMS / "P2_training" / "tightcorridor.txt"),
              load_room_file(ROOMS / "P1_training" / "Empty_room_3mx3mx3m_0.25m_cellsize.txt")]
     n_done = lockstep(oracle, rooms, n=1500, L=10, steps=650, seed=21, lanes=4, state_every=50)
     assert n_done > 1500
+
+
+def test_benched_path_full_size_with_truncation_wave(oracle):
+    """The exact thing bench.py times: nav3d_step (default lanes, programmatic dependent launch on) at 2^20 envs on
+    P1_training, 1 100 steps, so that the synchronous truncation wave of the 12x12x12 room at step 1 000 and the auto-resets
+    run at full size.  512 strided envs are replayed by the oracle EVERY step (observation, f64 reward, flags), invariants
+    are checked over all envs at intervals and at the end."""
+    import torch
+    from nav3d import Engine
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n, T, seed = 1 << 20, 1100, 2024
+    eng = Engine(n, rooms, local_map_length=10, seed=seed)
+    dev = eng.device
+    obs = eng.reset()
+    ids = np.arange(7, n, n // 512, dtype=np.uint32)
+    orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
+    ov = oracle.OracleVec(len(ids), orooms, 10, -2.0, seed, 0, True)
+    ov.set_ids(ids)
+    tid = torch.as_tensor(ids.astype(np.int64), device=dev)
+    assert np.array_equal(obs[tid].cpu().numpy().view(np.uint32), ov.reset().view(np.uint32))
+    rew = torch.zeros(n, device=dev); rew64 = torch.zeros(n, dtype=torch.float64, device=dev)
+    te = torch.zeros(n, dtype=torch.uint8, device=dev); tr = torch.zeros(n, dtype=torch.uint8, device=dev)
+    tobs = torch.zeros((n, 80), device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    free_t = torch.as_tensor(eng.room_free, device=dev)
+    n_done = n_done_all = 0
+    for t in range(T):
+        a = torch.randint(0, 6, (n,), generator=g, device=dev, dtype=torch.int64)
+        eng.step(a, obs, rew, te, tr, reward64=rew64, terminal_obs=tobs)
+        ov.step(a[tid].cpu().numpy())
+        assert np.array_equal(obs[tid].cpu().numpy().view(np.uint32), ov.obs.view(np.uint32)), f"obs t={t}"
+        assert np.array_equal(rew64[tid].cpu().numpy(), ov.reward), f"reward t={t}"
+        assert np.array_equal(te[tid].cpu().numpy(), ov.terminated) and np.array_equal(tr[tid].cpu().numpy(), ov.truncated), f"flags t={t}"
+        d = (ov.terminated | ov.truncated).astype(bool)
+        if d.any():
+            assert np.array_equal(tobs[tid].cpu().numpy()[d].view(np.uint32), ov.terminal_obs[d].view(np.uint32)), f"terminal obs t={t}"
+        n_done += int(d.sum())
+        if t in (998, 999, 1000) or t % 275 == 0 or t == T - 1:
+            st = eng.get_state()
+            free = free_t[st[:, 13].long()]
+            n_done_all += int((te | tr).sum())
+            assert bool(((obs >= 0) & (obs <= 1)).all()) and bool((obs[:, 64:68].sum(dim=1) == 1).all()) and bool((obs[:, 73:] == 0).all())
+            assert bool((st[:, 4] <= free).all()) and bool((st[:, 4] >= 1).all()) and bool((st[:, 6] < free).all())
+            assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
+    assert n_done > 50 and n_done_all > 100000          # a fifth of the envs play the 1 000-step room: they all end at step 1 000
+    st = eng.get_state()
+    assert np.array_equal(st[tid].cpu().numpy()[:, :15].astype(np.int64), ov.state())
+    for j in (0, 100, 511):
+        assert np.array_equal(eng.get_grid(int(ids[j])), np.minimum(ov.grid(j), 255).astype(np.int16))
 
 
 @pytest.mark.parametrize("lanes", [1, 4, 32])
