@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_co
 // touches stay in L1/L2 for the whole rollout, so DRAM sees the outputs the caller asked for plus one pass over the touched
 // lines.  When only the last observation is requested the intermediate observations are never formed.  The reset is an
 // out-of-line call (as in step_call_kernel) so that the loop body keeps the step's 64 registers.
-template <int G>
-__global__ void __launch_bounds__(kBlock, 6) rollout_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0,
+template <int G, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) rollout_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0,
                                                             float *obs, float *obs_last, float *reward, uint8_t *done,
                                                             uint8_t *actions_out, float *reward_scratch,
                                                             uint8_t *term_scratch, uint8_t *trunc_scratch) {
@@ -692,8 +692,8 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
         }
         switch (minb) {
             case 6: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 6>, e->P, io); break;
-            case 10: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 10>, e->P, io); break;
-            case 12: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 12>, e->P, io); break;
+            case 3: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 3>, e->P, io); break;
+            case 4: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 4>, e->P, io); break;
             default: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 8>, e->P, io); break;
         }
         return NAV3D_OK;
@@ -777,8 +777,18 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
     cudaStream_t s = (cudaStream_t)stream;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
-        rollout_kernel<G><<<grid_for(e->cfg.n_envs, G), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward, done,
-                                                                       actions_out, e->d_reward, e->d_term, e->d_trunc);
+        // tuning knobs: NAV3D_ROLLOUT_MINB = register budget, NAV3D_ROLLOUT_SMEM = dynamic shared memory per CTA (limits the
+        // resident CTAs per SM and with them the envs whose knowledge lines compete for L2)
+        static const int rminb = getenv("NAV3D_ROLLOUT_MINB") ? atoi(getenv("NAV3D_ROLLOUT_MINB")) : 6;
+        static const int rsmem = getenv("NAV3D_ROLLOUT_SMEM") ? atoi(getenv("NAV3D_ROLLOUT_SMEM")) : 0;
+        auto launch = [&](auto kern) {
+            if (rsmem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rsmem);
+            kern<<<grid_for(e->cfg.n_envs, G), kBlock, rsmem, s>>>(e->P, T, t0, obs, obs_last, reward, done, actions_out,
+                                                                    e->d_reward, e->d_term, e->d_trunc);
+        };
+        if (rminb == 3) launch(rollout_kernel<G, 3>);
+        else if (rminb == 4) launch(rollout_kernel<G, 4>);
+        else launch(rollout_kernel<G, 6>);
         return NAV3D_OK;
     });
     if (rc) return rc;

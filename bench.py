@@ -131,32 +131,63 @@ def c_port_rate(rooms, L, n_envs, T, threads):
     return n / dt
 
 
+def load_rooms_standalone(spec):
+    """The room grids WITHOUT importing the product package: nav3d/__init__.py dlopens libnav3d_b200.so, which the
+    reference arm must not map.  rooms.py itself only needs NumPy, so it is loaded as a lone module."""
+    import importlib.util
+    mspec = importlib.util.spec_from_file_location("nav3d_rooms_standalone", _nav3d_path.PKG_DIR / "nav3d" / "rooms.py")
+    mod = importlib.util.module_from_spec(mspec)
+    sys.modules[mspec.name] = mod
+    mspec.loader.exec_module(mod)
+    rooms = []
+    for d in spec["room_dirs"]:
+        rooms += mod.load_room_dir(ROOT / "rooms" / d, sort=True, simple=bool(spec.get("simple")))
+    return rooms
+
+
+def cpu_arm(spec, steps_per_worker, workers, one_process_steps=0):
+    """The CPU implementation of the path on this box's host cores, one env per worker process (the reference's own
+    SubprocVecEnv shape, train/Grid_Train.py:191-192).  kind "reference": the UNMODIFIED reference class from oracle/_ref
+    (staged by __graft_entry__.build() where /root/reference exists), resets and their file parse included (BASELINE.md §3);
+    kind "port": oracle/py_cubic.py, only when oracle/_ref is absent.  Returns (rate, wall, one_process_rate, kind, what)."""
+    from oracle import ref_runner
+    if ref_runner.available() and not spec.get("simple") and len(spec["room_dirs"]) == 1:
+        room_dir = ROOT / "rooms" / spec["room_dirs"][0]
+        rate, wall = ref_runner.reference_rate(room_dir, spec["L"], steps_per_worker, workers)
+        one = ref_runner.reference_rate(room_dir, spec["L"], one_process_steps, 1)[0] if one_process_steps else None
+        return rate, wall, one, "reference", ("the unmodified reference envs/CubicEnv.py GridAgent (oracle/_ref, behind the "
+                                               "gymnasium/matplotlib import shims of SURVEY Appendix A), reset(seed=42+rank) "
+                                               "then reset() on every episode end inside the timed region, stdout redirected")
+    grids = [r.grid.astype(int) for r in load_rooms_standalone(spec)]
+    rate, wall = python_port_rate(grids, spec["L"], steps_per_worker, workers)
+    one = python_port_rate(grids, spec["L"], one_process_steps, 1)[0] if one_process_steps else None
+    return rate, wall, one, "port", "oracle/py_cubic.py (Python port; oracle/_ref absent, so the reference itself could not be timed)"
+
+
 def run_reference(args):
-    """The reference arm: the reference's own CPU implementation of the path, all host cores.  The reference is a Python
-    class and /root/reference does not travel to the GPU box, so this times oracle/py_cubic.py (the Python port pinned to
-    the reference's golden traces), one env per worker process like the reference's SubprocVecEnv."""
+    """The reference arm: the reference's own CPU implementation of the path on all host cores — the unmodified
+    envs/CubicEnv.py class (oracle/_ref), one env per worker process like the reference's SubprocVecEnv.  Nothing of the
+    product (nav3d package, libnav3d_b200.so) is imported here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     spec = workload_spec(args.workload)
-    rooms = load_rooms(spec)
-    grids = [r.grid.astype(int) for r in rooms]
     cores = os.cpu_count() or 1
     K, W = args.steps, args.warmup
     # each "step" = every worker advances its env by S env-steps; S sized so the whole run takes about a minute
-    S = int(max(20, min(4000, 60.0 * 7000.0 / max(1, K + W))))
-    python_port_rate(grids, spec["L"], max(1, W * S // 4), cores)          # warm-up (fork, page-in)
-    t0 = time.perf_counter()
-    rate, wall = python_port_rate(grids, spec["L"], K * S, cores)
-    one, _ = python_port_rate(grids, spec["L"], min(K * S, 20000), 1)
+    S = int(max(20, min(4000, 60.0 * 5000.0 / max(1, K + W))))
+    cpu_arm(spec, max(1, W * S // 4), cores)                               # warm-up (fork, page-in)
+    rate, wall, one, kind, what = cpu_arm(spec, K * S, cores, one_process_steps=min(K * S, 10000))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
         "dtype": "python int/f64 (NumPy)", "data": "synthetic",
-        "config": {"workload": spec["desc"], "sample": f"{cores} worker processes x 1 env, {S} env-steps per worker per step"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"oracle/py_cubic.py, {cores} processes x {K * S} random-action steps with reset on done",
-                         "one_process": one},
+        "config": {"workload": spec["desc"],
+                   "sample": f"{cores} worker processes x 1 env, {S} env-steps per worker per step: a bounded CPU sample of the "
+                             f"{spec['envs_total']}-env workload (same rooms, L and action distribution; NOT the same env count)",
+                   "same_config": False},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{what}; {cores} processes x {K * S} random-action steps", "one_process": one},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -493,20 +524,17 @@ def main():
             torch.cuda.empty_cache()
         except Exception as ex:  # noqa: BLE001
             extra["fused_rollout_c4"] = {"error": str(ex)}
-        # CPU baseline on this box's host cores (bounded sample)
+        # CPU baseline on this box's host cores (bounded sample): the reference itself when oracle/_ref travelled here
         cores = os.cpu_count() or 1
-        grids = [r.grid.astype(int) for r in rooms]
-        per_worker = 30000
-        py_all, wall = python_port_rate(grids, L, per_worker, cores)
-        py_one, _ = python_port_rate(grids, L, 20000, 1)
+        per_worker = 12000
+        cb_rate, cb_wall, cb_one, cb_kind, cb_what = cpu_arm(spec, per_worker, cores, one_process_steps=10000)
         c_all = c_port_rate(rooms, L, 4096, 100, cores)
         c_one = c_port_rate(rooms, L, 512, 100, 1)
-        cpu_baseline = {"value": py_all, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"oracle/py_cubic.py (Python port of the reference env, pinned to its golden traces): {cores} "
-                                  f"worker processes x 1 env x {per_worker} random-action steps, reset on done ({wall:.1f} s)",
-                        "one_process": py_one,
+        cpu_baseline = {"value": cb_rate, "unit": UNIT, "cores": cores, "kind": cb_kind,
+                        "sample": f"{cb_what}; {cores} worker processes x 1 env x {per_worker} random-action steps ({cb_wall:.1f} s)",
+                        "one_process": cb_one,
                         "c_port": {"value": c_all, "cores": cores, "one_thread": c_one,
-                                   "sample": "oracle/nav3d_oracle.c: 4096 envs x 100 steps, pthreads"}}
+                                   "sample": "oracle/nav3d_oracle.c (C restatement, the parity checker): 4096 envs x 100 steps, pthreads"}}
 
     if rank == 0:
         line = {
