@@ -190,6 +190,16 @@ NAV3D_HD void store_stream(float *p, float v) {
 #endif
 }
 
+// Observation rows.  Direct: a lane streams its float4 straight to the caller's row.  STAGED (thread-per-env kernels): the
+// row is first assembled in the thread's slot of a shared-memory staging tile (kStageStride floats apart: 84 mod 32 = 20
+// spreads the 32 rows' float4 over all banks) and the WARP then writes the 32 rows out with fully coalesced 128-bit stores
+// (flush_rows in nav3d_engine.cu) — 16 full sectors per store instruction instead of 32 half sectors.
+constexpr int kStageStride = 84;
+template <bool STAGED> NAV3D_HD void row_store(float *row, int j, float4 v) {
+    if (STAGED) reinterpret_cast<float4 *>(row)[j] = v;
+    else store_stream(reinterpret_cast<float4 *>(row) + j, v);
+}
+
 template <int G> NAV3D_HD unsigned group_mask(int lane_in_warp) {
     return (G >= 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane_in_warp & ~(G - 1) & 31);
 }
@@ -356,7 +366,7 @@ NAV3D_HD uint32_t window_quad(uint32_t lo, uint32_t hi, int s) {
 }
 
 // Steps 3-6 of get_obs: the 9 scalars + zero padding = 4 more float4 (:279-307)
-template <int G>
+template <int G, bool STAGED = false>
 NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &sc, const float *lut,
                             float *__restrict__ obs_row) {
     for (int j = 16 + lane; j < 20; j += G) {
@@ -378,7 +388,7 @@ NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &s
         } else {
             v.x = v.y = v.z = v.w = 0.f;
         }
-        store_stream(reinterpret_cast<float4 *>(obs_row) + j, v);
+        row_store<STAGED>(obs_row, j, v);
     }
 }
 
@@ -425,7 +435,7 @@ NAV3D_HD void centre_update(uint32_t *cw, int nzb, int z, int c_new, bool mark, 
 //            left lies one step back on that axis and its rays along the axis already covered everything this cell's rays
 //            cover except the single cell at distance exactly L ahead: that run shrinks to the one far cell.
 // Returns this lane's share of the neighbour codes (OR over the group = EnvState::nbr).
-template <int G>
+template <int G, bool STAGED = false>
 NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z,
                           const Rays &r, int c_new, bool fresh, bool persist, int mdir, const ObsScalars &sc,
                           const float *lut, float *__restrict__ obs_row) {
@@ -463,45 +473,44 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
     else if (mdir == 3) { my1 = r.y0; my0 = (y - r.y0 == L) ? r.y0 : r.y0 + 1; }
     else if (mdir == 4) { mz0 = r.z1; mz1 = (r.z1 - z == L) ? r.z1 : r.z1 - 1; }
     else if (mdir == 5) { mz1 = r.z0; mz0 = (z - r.z0 == L) ? r.z0 : r.z0 + 1; }
-    // cells of the x run: cx in [mx0, mx1] \ {x}; of the y run: cy in [my0, my1] \ {y}
-    const int cntx = (mx1 >= mx0) ? (mx1 - mx0 + 1) - ((x >= mx0 && x <= mx1) ? 1 : 0) : 0;
-    const int cnty = (my1 >= my0) ? (my1 - my0 + 1) - ((y >= my0 && y <= my1) ? 1 : 0) : 0;
-    const int total = mark ? cntx + cnty : 0;
+    // Free cells of the x run (row y) and of the y run (column x) become "seen"; a run's wall end is a point mark.  The
+    // centre column is skipped (its owner writes it).  Lane-strided, U cells per lane per chunk, loads before stores.
     const int zbz = div6(z), zsh = 5 * (z - 6 * zbz);
     const uint32_t zoffz = (uint32_t)zbz << 4;
     const uint32_t xpc = k_xpart(R, x + kPadLo), ypc = k_ypart(R, y + kPadLo);
-    constexpr int RC = G >= 8 ? 2 : (G == 4 ? 6 : 8);     // marked cells per lane per chunk: loads of a chunk overlap
-    int midx[RC];
-    uint32_t mold[RC], mcode[RC];
-    auto mark_load = [&](int base) {
+    const bool hasx = mark && mx1 >= mx0, hasy = mark && my1 >= my0;
+    const bool wxh = hasx && (r.wall6 & 1u) && mx1 == r.x1, wxl = hasx && (r.wall6 & 2u) && mx0 == r.x0;
+    const bool wyh = hasy && (r.wall6 & 4u) && my1 == r.y1, wyl = hasy && (r.wall6 & 8u) && my0 == r.y0;
+    const int fx0 = mx0 + (wxl ? 1 : 0), fx1 = hasx ? mx1 - (wxh ? 1 : 0) : fx0 - 1;
+    const int fy0 = my0 + (wyl ? 1 : 0), fy1 = hasy ? my1 - (wyh ? 1 : 0) : fy0 - 1;
+    const uint32_t xmul = (uint32_t)R.nzb << 4, ymul = (uint32_t)(R.ntx * R.nzb) << 4;
+    const uint32_t xbase = ypc + zoffz, ybase = xpc + zoffz;
+    constexpr int U = G >= 8 ? 2 : (G == 4 ? 4 : 8);
+    // (the word index of a run cell is recomputed for the store instead of being kept alive across the loads' latency)
+    auto run_idx = [&](int c, uint32_t mul, int sft, uint32_t base) {
+        const int t = c + kPadLo;
+        return base + (uint32_t)(t >> 2) * mul + ((uint32_t)(t & 3) << sft);
+    };
+    uint32_t xw[U], yw[U], pw[4];
+    auto run_load = [&](int first, int c1, int skip, uint32_t mul, int sft, uint32_t base, uint32_t *w) {
 #pragma unroll
-        for (int k = 0; k < RC; k++) {
-            const int i = base + k * G + lane;
-            int id = -1;
-            uint32_t code = kCodeSeen;
-            if (i < cntx) {
-                int cx = mx0 + i;
-                if (x >= mx0 && cx >= x) cx++;                                   // skip the centre column
-                id = (int)(k_xpart(R, cx + kPadLo) + ypc + zoffz);
-                if ((cx == r.x1 && (r.wall6 & 1u)) || (cx == r.x0 && (r.wall6 & 2u))) code = kCodeWall;
-            } else if (i < total) {
-                int cy = my0 + (i - cntx);
-                if (y >= my0 && cy >= y) cy++;
-                id = (int)(xpc + k_ypart(R, cy + kPadLo) + zoffz);
-                if ((cy == r.y1 && (r.wall6 & 4u)) || (cy == r.y0 && (r.wall6 & 8u))) code = kCodeWall;
-            }
-            midx[k] = id; mcode[k] = code;
-            mold[k] = id >= 0 ? K[id] : 0u;
+        for (int u = 0; u < U; u++) {
+            const int c = first + lane + u * G;
+            w[u] = (c <= c1 && c != skip) ? K[run_idx(c, mul, sft, base)] : 0xffffffffu;   // all ones: nothing to mark
         }
     };
-    auto mark_store = [&]() {
+    auto run_store = [&](int first, uint32_t mul, int sft, uint32_t base, const uint32_t *w) {
 #pragma unroll
-        for (int k = 0; k < RC; k++) {
-            const uint32_t n = mark_field(mold[k], zsh, mcode[k]);
-            if (midx[k] >= 0 && n != mold[k]) K[midx[k]] = n;
-        }
+        for (int u = 0; u < U; u++)
+            if (((w[u] >> zsh) & 31u) == 0u) K[run_idx(first + lane + u * G, mul, sft, base)] = w[u] | (kCodeSeen << zsh);
     };
-    if (total > 0) mark_load(0);
+    run_load(fx0, fx1, x, xmul, 2, xbase, xw);
+    run_load(fy0, fy1, y, ymul, 0, ybase, yw);
+    const bool pon[4] = {wxh, wxl, wyh, wyl};
+    const uint32_t pidx[4] = {k_xpart(R, r.x1 + kPadLo) + xbase, k_xpart(R, r.x0 + kPadLo) + xbase,
+                              k_ypart(R, r.y1 + kPadLo) + ybase, k_ypart(R, r.y0 + kPadLo) + ybase};
+#pragma unroll
+    for (int d = 0; d < 4; d++) pw[d] = (pon[d] && (d & (G - 1)) == lane) ? K[pidx[d]] : 0xffffffffu;
     // The owner of the centre column loads all of its words: counter update + the z rays.
     bool owner = false;
 #pragma unroll
@@ -522,9 +531,17 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
 #pragma unroll
         for (int b = 0; b < 3; b++) if (b < nzb && persist && cw[b] != cw_old[b]) K[cbase + ((uint32_t)b << 4)] = cw[b];
     }
-    if (total > 0) {
-        mark_store();
-        for (int base = G * RC; base < total; base += G * RC) { mark_load(base); mark_store(); }
+    run_store(fx0, xmul, 2, xbase, xw);
+    run_store(fy0, ymul, 0, ybase, yw);
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+        if (((pw[d] >> zsh) & 31u) == 0u) K[pidx[d]] = pw[d] | (kCodeWall << zsh);
+    // the rest of long runs, both runs per round so that their loads share one latency
+    for (int k = G * U; fx0 + k <= fx1 || fy0 + k <= fy1; k += G * U) {
+        run_load(fx0 + k, fx1, x, xmul, 2, xbase, xw);
+        run_load(fy0 + k, fy1, y, ymul, 0, ybase, yw);
+        run_store(fx0 + k, xmul, 2, xbase, xw);
+        run_store(fy0 + k, ymul, 0, ybase, yw);
     }
 
     // ---- 3. the window: clip to [-2, 20], (m + 2) / 22 (:273-275), one float4 per column; neighbour codes
@@ -564,12 +581,12 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
                     float4 v;
                     v.x = lut[quad & 31u]; v.y = lut[(quad >> 5) & 31u];
                     v.z = lut[(quad >> 10) & 31u]; v.w = lut[quad >> 15];
-                    store_stream(reinterpret_cast<float4 *>(obs_row) + (dxi * 4 + dyi), v);
+                    row_store<STAGED>(obs_row, dxi * 4 + dyi, v);
                 }
             }
         }
     }
-    if (obs_row != nullptr) write_scalars<G>(P, lane, sc, lut, obs_row);
+    if (obs_row != nullptr) write_scalars<G, STAGED>(P, lane, sc, lut, obs_row);
     return nbr;
 }
 
@@ -588,7 +605,7 @@ NAV3D_HD void reset_clear(const EngineParams &P, int env, int lane, uint32_t roo
     for (uint32_t i = lane; i < n; i += G) k4[i] = zero;
 }
 
-template <int G>
+template <int G, bool STAGED = false>
 NAV3D_HD uint32_t reset_lane(const EngineParams &P, int env, int lane, uint32_t room_idx, uint32_t k,
                              uint32_t episode_after, const float *lut, float *obs_row, ResetCtx &c) {
     const RoomDev R = P.rooms[room_idx];
@@ -605,7 +622,7 @@ NAV3D_HD uint32_t reset_lane(const EngineParams &P, int env, int lane, uint32_t 
     sc.facing = 0; sc.last_action = 0; sc.was_near_wall = 0; sc.last_bump = 0; sc.down = c.r.down;
     sc.visited = 1; sc.total_free = R.n_free;
     // internal_grid[start] = 1 (:85), then the first sensing pass
-    return observe<G>(P, R, envk, lane, c.x, c.y, c.z, c.r, 1, true, true, -1, sc, lut, obs_row);
+    return observe<G, STAGED>(P, R, envk, lane, c.x, c.y, c.z, c.r, 1, true, true, -1, sc, lut, obs_row);
 }
 
 NAV3D_HD void reset_commit(const EngineParams &P, int env, int lane, const ResetCtx &c, uint32_t nbr) {
@@ -659,9 +676,12 @@ struct StepCtx {                   // what the second half needs; identical in e
 
 // REG_STATE (fused multi-step rollouts): the env's record lives in the caller's registers (`rs`, every lane holds a
 // copy and every lane computes the new one) instead of making a round trip through global memory each step.
-template <int G, bool REG_STATE = false>
+// STAGED (G == 1): the observation row is assembled in `stage_row` (shared memory) and `*dst_slot` receives the global row
+// it belongs to (obs or terminal_obs; NULL = nobody reads it); the warp writes it out afterwards.
+template <int G, bool REG_STATE = false, bool STAGED = false>
 NAV3D_HD uint32_t step_lane(const EngineParams &P, const StepIO &io, int env, int lane, int action, const float *lut,
-                            long long row /* row index for the output arrays */, const EnvState *rs, StepCtx &c) {
+                            long long row /* row index for the output arrays */, const EnvState *rs, StepCtx &c,
+                            float *stage_row = nullptr, float **dst_slot = nullptr) {
     const EnvState st = REG_STATE ? *rs : P.states[env];
     const RoomDev R = P.rooms[st.room];
     uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
@@ -716,8 +736,10 @@ NAV3D_HD uint32_t step_lane(const EngineParams &P, const StepIO &io, int env, in
     ObsScalars sc;
     sc.facing = facing; sc.last_action = st.last_action; sc.was_near_wall = (flags & kWasNearWall) != 0;
     sc.last_bump = (flags & kLastBump) != 0; sc.down = r.down; sc.visited = c.visited; sc.total_free = R.n_free;
+    if (STAGED) { *dst_slot = orow; if (orow != nullptr) orow = stage_row; }
     if (c.will_reset && orow == nullptr) return 0u;        // nothing observes the last state of the episode
-    return observe<G>(P, R, envk, lane, x, y, z, r, c.c_new, c.explored, !c.will_reset, moved ? (int)dir : -2, sc, lut, orow);
+    return observe<G, STAGED>(P, R, envk, lane, x, y, z, r, c.c_new, c.explored, !c.will_reset, moved ? (int)dir : -2, sc,
+                              lut, orow);
 }
 
 template <int G, bool REG_STATE = false>
@@ -751,7 +773,7 @@ NAV3D_HD void step_commit(const EngineParams &P, const StepIO &io, int env, int 
     const int ret_centi = st.ret_centi + cents;
 
     if (writer) {
-        store_stream(io.reward + row, (float)rew);
+        if (!REG_STATE || io.reward) store_stream(io.reward + row, (float)rew);
         if (io.reward64) io.reward64[row] = rew;
         if (!REG_STATE || io.terminated) io.terminated[row] = c.done ? 1 : 0;
         if (!REG_STATE || io.truncated) io.truncated[row] = c.truncated ? 1 : 0;
@@ -777,11 +799,12 @@ NAV3D_HD void step_commit(const EngineParams &P, const StepIO &io, int env, int 
 }
 
 // Returns true when the env finished its episode and must be reset by the caller (auto_reset).
-template <int G, bool REG_STATE = false>
+template <int G, bool REG_STATE = false, bool STAGED = false>
 NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
-                       const float *lut, long long row, EnvState *rs = nullptr, uint32_t *done_bits = nullptr) {
+                       const float *lut, long long row, EnvState *rs = nullptr, uint32_t *done_bits = nullptr,
+                       float *stage_row = nullptr, float **dst_slot = nullptr) {
     StepCtx c;
-    const uint32_t part = step_lane<G, REG_STATE>(P, io, env, lane, action, lut, row, rs, c);
+    const uint32_t part = step_lane<G, REG_STATE, STAGED>(P, io, env, lane, action, lut, row, rs, c, stage_row, dst_slot);
     step_commit<G, REG_STATE>(P, io, env, lane, c, group_or<G>(part, lane_in_warp), row, rs, done_bits);
     return c.will_reset;
 }

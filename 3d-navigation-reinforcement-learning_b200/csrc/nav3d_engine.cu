@@ -174,6 +174,161 @@ __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Thread-per-env kernels (CubicEnv, lanes_per_env = 1): nothing of a step is computed twice, every load of a step is issued
+// by the one thread that needs it, and the only cooperation is in data movement — the warp writes the 32 observation rows
+// it assembled in shared memory with coalesced 128-bit stores, and clears the knowledge of the envs it resets together.
+// ---------------------------------------------------------------------------------------------------------------
+// The warp's 32 staged rows -> their global rows (dst[e] == NULL: env e has none).  8 envs x 20 float4 = 5 x 32 float4.
+__device__ __forceinline__ void flush_rows(const float *stage, float *const *dst, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const int idx = i * 32 + lane, e8 = idx / 20, j = idx - e8 * 20;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int e = g * 8 + e8;
+            float *d = dst[e];
+            if (d != nullptr)
+                __stcs(reinterpret_cast<float4 *>(d) + j, reinterpret_cast<const float4 *>(stage + e * kStageStride)[j]);
+        }
+    }
+    __syncwarp();
+}
+
+// Auto-reset of the warp's envs whose lanes say `mine` (CubicEnv.py:77-108 with Philox picks).  Out of line so that the
+// step keeps its registers.  The new record goes to P.states.
+template <bool STAGED>
+__device__ __noinline__ void tpe_reset(const EngineParams &P, bool mine, uint32_t env, uint32_t episode, bool have_picks,
+                                       uint32_t room, uint32_t k, const float *lut, float *obs, float *stage,
+                                       float **dst, int lane) {
+    const unsigned rmask = __ballot_sync(0xffffffffu, mine);
+    if (mine && !have_picks) reset_picks(P, (int)env, episode, room, k);
+    // internal_grid = full(-1) (:84): the whole warp sweeps each env's bricks
+    for (unsigned m = rmask; m; m &= m - 1u) {
+        const int src = __ffs((int)m) - 1;
+        const uint32_t e = __shfl_sync(0xffffffffu, env, src), r = __shfl_sync(0xffffffffu, room, src);
+        const uint32_t n = k_bytes(P.rooms[r]) >> 4;
+        uint4 *k4 = reinterpret_cast<uint4 *>(P.know + (unsigned long long)e * P.env_stride);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = (uint32_t)lane; i < n; i += 32u) k4[i] = zero;
+    }
+    __syncwarp();
+    if (STAGED) dst[lane] = nullptr;
+    if (mine) {
+        ResetCtx c;
+        float *row = obs ? obs + (unsigned long long)env * kObsDim : nullptr;
+        if (STAGED) { dst[lane] = row; if (row) row = stage + lane * kStageStride; }
+        const uint32_t nbr = reset_lane<1, STAGED>(P, (int)env, 0, room, k, episode + 1u, lut, row, c);
+        reset_commit(P, (int)env, 0, c, nbr);
+    }
+    if (STAGED) flush_rows(stage, dst, lane);
+}
+
+template <int MINB, bool STAGED>
+__global__ void __launch_bounds__(kBlock, MINB) step_tpe_kernel(const __grid_constant__ EngineParams P, StepIO io) {
+    __shared__ float lut[kLutSize];
+    __shared__ __align__(16) float stage_all[STAGED ? kBlock * kStageStride : 4];
+    __shared__ float *dst_all[STAGED ? kBlock : 1];
+    asm volatile("griddepcontrol.launch_dependents;");          // programmatic dependent launch, as in step_call_kernel
+    fill_lut(lut, P.L);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    float *stage = stage_all + wbase * kStageStride;
+    float **dst = dst_all + wbase;
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (gid - lane >= io.env_n) return;                          // the whole warp is past the range
+    const bool valid = gid < io.env_n;
+    const long long env = io.env0 + gid;
+    if (STAGED) dst[lane] = nullptr;
+    bool rst = false;
+    if (valid)
+        rst = step_env<1, false, STAGED>(P, io, (int)env, 0, lane, (int)io.actions[env], lut, env, nullptr, nullptr,
+                                         stage + lane * kStageStride, dst + lane);
+    if (STAGED) flush_rows(stage, dst, lane);
+    if (__any_sync(0xffffffffu, rst)) {
+        const uint32_t episode = rst ? P.states[env].episode : 0u;   // untouched by a step that ends its episode
+        tpe_reset<STAGED>(P, rst, (uint32_t)env, episode, false, 0u, 0u, lut, io.obs, stage, dst, lane);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) reset_tpe_kernel(const __grid_constant__ EngineParams P,
+                                                           const int32_t *__restrict__ env_ids, int n,
+                                                           const int32_t *__restrict__ picks, float *obs) {
+    __shared__ float lut[kLutSize];
+    __shared__ __align__(16) float stage_all[kBlock * kStageStride];
+    __shared__ float *dst_all[kBlock];
+    fill_lut(lut, P.L);
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx - lane >= n) return;
+    int env = idx < n ? (env_ids ? env_ids[idx] : (int)idx) : -1;
+    const bool mine = env >= 0 && env < P.n_envs;
+    uint32_t episode = 0, room = 0, k = 0;
+    if (mine) {
+        episode = P.states[env].episode;
+        if (picks) {
+            room = (uint32_t)picks[2 * idx];
+            room = room < (uint32_t)P.n_rooms ? room : (uint32_t)P.n_rooms - 1u;
+            const uint32_t nf = P.rooms[room].n_free;
+            k = (uint32_t)picks[2 * idx + 1];
+            k = k < nf ? k : nf - 1u;
+        }
+    }
+    tpe_reset<true>(P, mine, (uint32_t)env, episode, picks != nullptr, room, k, lut, obs, stage_all + wbase * kStageStride,
+                    dst_all + wbase, lane);
+}
+
+// T fused steps per env, thread per env (on-device Philox actions).  The record stays in the
+// thread's registers for the whole rollout and the knowledge lines it touches stay in L2, so DRAM sees the outputs the
+// caller asked for plus one pass over the touched lines.
+template <int MINB, bool STAGED>
+__global__ void __launch_bounds__(kBlock, MINB) rollout_tpe_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0,
+                                                                   float *obs, float *obs_last, float *reward, uint8_t *done,
+                                                                   uint8_t *actions_out) {
+    __shared__ float lut[kLutSize];
+    __shared__ __align__(16) float stage_all[STAGED ? kBlock * kStageStride : 4];
+    __shared__ float *dst_all[STAGED ? kBlock : 1];
+    fill_lut(lut, P.L);
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    float *stage = stage_all + wbase * kStageStride;
+    float **dst = dst_all + wbase;
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long N = P.n_envs;
+    if (gid - lane >= N) return;
+    const bool valid = gid < N;
+    const long long env = gid;
+    EnvState st;
+    if (valid) st = P.states[env];
+    for (int t = 0; t < T; t++) {
+        StepIO io;
+        io.actions = nullptr;
+        // obs == NULL: only the last step's observation is written out
+        io.obs = obs ? obs + (long long)t * N * kObsDim : (t == T - 1 ? obs_last : nullptr);
+        io.reward = reward ? reward + (long long)t * N : nullptr;
+        io.reward64 = nullptr; io.terminated = nullptr; io.truncated = nullptr;
+        io.terminal_obs = nullptr; io.episodes = nullptr;
+        io.env0 = 0; io.env_n = P.n_envs;
+        if (STAGED) dst[lane] = nullptr;
+        bool rst = false;
+        if (valid) {
+            uint32_t u0, u1, bits = 0;
+            philox4x32_10(P.env_id0 + (uint32_t)env, t0 + (uint32_t)t, 0u, kStreamAction, P.seed_lo, P.seed_hi, u0, u1);
+            const int action = (int)mulhi_range(u0, 6u);
+            rst = step_env<1, true, STAGED>(P, io, (int)env, 0, lane, action, lut, env, &st, &bits,
+                                            stage + lane * kStageStride, dst + lane);
+            if (done) done[(long long)t * N + env] = bits ? 1 : 0;
+            if (actions_out) actions_out[(long long)t * N + env] = (uint8_t)action;
+        }
+        if (STAGED) flush_rows(stage, dst, lane);
+        if (__any_sync(0xffffffffu, rst)) {
+            tpe_reset<STAGED>(P, rst, (uint32_t)env, st.episode, false, 0u, 0u, lut, io.obs, stage, dst, lane);
+            if (rst) st = P.states[env];           // the new episode's record (written by this very thread)
+        }
+    }
+    if (valid) P.states[env] = st;
+}
+
 // T fused steps per env with on-device Philox actions.  An env's record and the knowledge lines it
 // touches stay in L1/L2 for the whole rollout, so DRAM sees the outputs the caller asked for plus one pass over the touched
 // lines.  When only the last observation is requested the intermediate observations are never formed.  The reset is an
@@ -656,7 +811,9 @@ int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_
     NvtxRange range("nav3d_reset");
     e->reset_seen = true;
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = dispatch_lanes(e->G, [&](auto g) {
+    int rc = NAV3D_OK;
+    if (!e->simple && e->G == 1) reset_tpe_kernel<<<grid_for(n, 1), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
+    else rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         if (e->simple) simple_reset_kernel<G><<<grid_for(n, G), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
         else reset_kernel<G><<<grid_for(n, G), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
@@ -688,6 +845,21 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
         if (e->simple) {
             if (minb == 6) cudaLaunchKernelEx(&cfg, simple_step_kernel<G, 6>, e->P, io);
             else cudaLaunchKernelEx(&cfg, simple_step_kernel<G, 8>, e->P, io);
+            return NAV3D_OK;
+        }
+        if (G == 1) {                                  // thread per env: staged, coalesced observation stores
+            static const bool staged = !(getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) == 0);
+            switch (minb * 2 + (staged ? 1 : 0)) {
+                case 6: cudaLaunchKernelEx(&cfg, step_tpe_kernel<3, false>, e->P, io); break;
+                case 7: cudaLaunchKernelEx(&cfg, step_tpe_kernel<3, true>, e->P, io); break;
+                case 10: cudaLaunchKernelEx(&cfg, step_tpe_kernel<5, false>, e->P, io); break;
+                case 11: cudaLaunchKernelEx(&cfg, step_tpe_kernel<5, true>, e->P, io); break;
+                case 12: cudaLaunchKernelEx(&cfg, step_tpe_kernel<6, false>, e->P, io); break;
+                case 13: cudaLaunchKernelEx(&cfg, step_tpe_kernel<6, true>, e->P, io); break;
+                default:
+                    if (staged) cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, true>, e->P, io);
+                    else cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, false>, e->P, io);
+            }
             return NAV3D_OK;
         }
         switch (minb) {
@@ -786,6 +958,25 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
             kern<<<grid_for(e->cfg.n_envs, G), kBlock, rsmem, s>>>(e->P, T, t0, obs, obs_last, reward, done, actions_out,
                                                                     e->d_reward, e->d_term, e->d_trunc);
         };
+        if (G == 1) {
+            auto launch1 = [&](auto kern) {
+                if (rsmem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rsmem);
+                kern<<<grid_for(e->cfg.n_envs, 1), kBlock, rsmem, s>>>(e->P, T, t0, obs, obs_last, reward, done, actions_out);
+            };
+            static const bool staged = getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) != 0;
+            switch (rminb * 2 + (staged ? 1 : 0)) {
+                case 6: launch1(rollout_tpe_kernel<3, false>); break;
+                case 7: launch1(rollout_tpe_kernel<3, true>); break;
+                case 10: launch1(rollout_tpe_kernel<5, false>); break;
+                case 11: launch1(rollout_tpe_kernel<5, true>); break;
+                case 12: launch1(rollout_tpe_kernel<6, false>); break;
+                case 13: launch1(rollout_tpe_kernel<6, true>); break;
+                default:
+                    if (staged) launch1(rollout_tpe_kernel<4, true>);
+                    else launch1(rollout_tpe_kernel<4, false>);
+            }
+            return NAV3D_OK;
+        }
         if (rminb == 3) launch(rollout_kernel<G, 3>);
         else if (rminb == 4) launch(rollout_kernel<G, 4>);
         else launch(rollout_kernel<G, 6>);

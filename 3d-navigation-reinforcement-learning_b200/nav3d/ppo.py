@@ -327,7 +327,10 @@ class RecurrentPPO:
                 self._upd_stream = torch.cuda.Stream(device=self.device)
             for k, v in fresh.items():
                 self._upd[k].copy_(v)
-            data, acc, cuts = self._upd, self._upd_acc, (0,)
+            # cuts=None = mask the LSTM state at EVERY timestep: while a graph is being captured the policy runs torch's
+            # LSTM between cuts (policy._run_lstm excludes the fused kernel then), and the replayed minibatches differ in
+            # where their episodes start, so no fixed cut list would be right for all of them.
+            data, acc, cuts = self._upd, self._upd_acc, None
             acc.zero_()
             # everything of a captured minibatch lives on ONE stream (also the warm-up runs, so that autograd's gradient
             # accumulators are bound to the capture stream and not to the policy's side stream)

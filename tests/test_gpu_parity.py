@@ -417,6 +417,35 @@ def test_scalar_facade_matches_reference_traces(cubic_traces, capsys):
     capsys.readouterr()
 
 
+def test_scalar_facade_render_text_matches_reference(capsys):
+    """a11: render() in text mode (CubicEnv.py:475-499) prints exactly what the unmodified reference printed
+    (tests/golden/render_text.json, written by tests/golden/make_render_golden.py); close() releases the engine."""
+    import json
+    from pathlib import Path
+
+    from envs.CubicEnv import GridAgent
+    g = json.loads((Path(__file__).parent / "golden" / "render_text.json").read_text())
+    p = ROOMS / g["room"]
+    env = GridAgent(room_path=str(p.parent), local_map_length=g["L"], render_mode="human")
+    env.rooms = [Path(p)]
+    env.reset(seed=g["seed"])
+    capsys.readouterr()
+    env.render()
+    assert capsys.readouterr().out == g["frames"]["0"]
+    actions = np.random.default_rng(g["action_seed"]).integers(0, 6, size=120)
+    for t, a in enumerate(actions, 1):
+        env.step(int(a))
+        if str(t) in g["frames"]:
+            capsys.readouterr()
+            env.render()
+            assert capsys.readouterr().out == g["frames"][str(t)], f"frame after step {t}"
+    env.render_mode = None
+    env.render()                                   # any other mode: no output (:480-481)
+    assert capsys.readouterr().out == ""
+    env.close()
+    env.close()                                    # idempotent
+
+
 def test_batched_vec_env_contract(oracle):
     """nav3d.BatchedCubicEnv: SB3 VecEnv-shaped API (reset/step_async/step_wait, dones, terminal_observation, episode)."""
     import torch

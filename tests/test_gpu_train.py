@@ -274,3 +274,42 @@ def test_cuda_graph_update_equals_eager_update():
             c.collect_rollouts(); c.train()
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_cuda_graph_update_masks_episode_starts_inside_a_chunk():
+    """episodes that end in the middle of a sequence chunk.  A 5x6x5 room has 36 free cells, so every
+    episode is truncated after 36 steps and each 64-step chunk holds one or two resets; the replayed (graph) update
+    must zero the LSTM state there exactly like the eager update: same losses, same parameters."""
+    import numpy as np
+    from edge_rooms import rooms_from_grids
+    from nav3d import BatchedCubicEnv
+    from nav3d.ppo import RecurrentPPO
+    g = np.zeros((5, 6, 5), dtype=np.int8)
+    g[0], g[-1], g[:, 0], g[:, -1], g[:, :, 0], g[:, :, -1] = -2, -2, -2, -2, -2, -2
+    rooms = rooms_from_grids([g])
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        models = []
+        for graph in (False, True):
+            env = BatchedCubicEnv(rooms=rooms, num_envs=8, local_map_length=10, seed=5)
+            models.append(RecurrentPPO(env, policy_kwargs=dict(net_arch=dict(pi=[64, 64], vf=[64, 64]), lstm_hidden_size=64),
+                                       n_steps=64, batch_size=64, n_epochs=2, ent_coef=0.01, seed=3, cuda_graph=graph,
+                                       allow_tf32=False))
+        a, b = models
+        for it in range(2):
+            for m in models:
+                m.collect_rollouts()
+            assert torch.equal(a._actions, b._actions), it
+            starts = a._starts.view(64, 8)
+            assert int(starts[1:].sum()) >= 8                      # resets strictly inside the chunks
+            sa, sb = a.train(), b.train()
+            pa = torch.cat([p.detach().flatten() for p in a.policy.parameters()])
+            pb = torch.cat([p.detach().flatten() for p in b.policy.parameters()])
+            rel = float((pa - pb).norm() / pa.norm())
+            assert rel < 5e-4, (it, rel)
+            for k in ("policy_loss", "value_loss", "entropy_loss", "approx_kl"):
+                assert abs(sa[k] - sb[k]) <= 1e-3 * (1.0 + abs(sa[k])), (k, sa[k], sb[k])
+        assert b._upd_graph is not None and a._upd_graph is None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old

@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--T", type=int, default=32)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--reps", type=int, default=6)
+    ap.add_argument("--only", default="", help="run only the variant whose name contains this")
+    ap.add_argument("--preroll", type=int, default=0, help="untimed fused steps before the measurement (episode age)")
     args = ap.parse_args()
     import torch
     from nav3d import Engine
@@ -33,7 +35,13 @@ def main():
     if n * T * 320 < 40e9:
         variants["all_obs+reward+done"] = dict(obs=torch.empty((T, n, 80), dtype=torch.float32, device=dev), reward=rew, done=done)
     t0 = 0
+    if args.preroll:
+        for _ in range(args.preroll // T):
+            eng.rollout_random(T, t0, obs_last=obs_last); t0 += T
+        out["preroll"] = t0
     for name, kw in variants.items():
+        if args.only and args.only not in name:
+            continue
         eng.rollout_random(T, t0, **kw); t0 += T
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
