@@ -485,27 +485,51 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
     const int fy0 = my0 + (wyl ? 1 : 0), fy1 = hasy ? my1 - (wyh ? 1 : 0) : fy0 - 1;
     const uint32_t xmul = (uint32_t)R.nzb << 4, ymul = (uint32_t)(R.ntx * R.nzb) << 4;
     const uint32_t xbase = ypc + zoffz, ybase = xpc + zoffz;
-    constexpr int U = G >= 8 ? 2 : (G == 4 ? 4 : 8);
-    // (the word index of a run cell is recomputed for the store instead of being kept alive across the loads' latency)
-    auto run_idx = [&](int c, uint32_t mul, int sft, uint32_t base) {
-        const int t = c + kPadLo;
-        return base + (uint32_t)(t >> 2) * mul + ((uint32_t)(t & 3) << sft);
+    // Tile by tile: the four cells of a run inside one 4x4-column tile are the words tile + 4j (x run) or tile + j (y run:
+    // one 128-bit load), so a cell costs no address arithmetic.  Lane-strided over the tiles, UT tiles per lane per run
+    // per round; a word that is not to be marked reads as all ones ("nothing to do").
+    constexpr int UT = G >= 4 ? 1 : (G == 2 ? 2 : 3);
+    const int xt0 = (fx0 + kPadLo) >> 2, xt1 = fx1 >= fx0 ? (fx1 + kPadLo) >> 2 : xt0 - 1;
+    const int yt0 = (fy0 + kPadLo) >> 2, yt1 = fy1 >= fy0 ? (fy1 + kPadLo) >> 2 : yt0 - 1;
+    // bit j: cell 4T - pad + j of tile T lies in [c_lo, c_hi] and is not the centre
+    auto tile_mask = [&](int T, int c_lo, int c_hi, int skip) {
+        const int c0 = 4 * T - kPadLo;
+        const int lo_ = imin(imax(c_lo - c0, 0), 4), up = imin(imax(c0 + 3 - c_hi, 0), 4);
+        uint32_t m = (0xfu << lo_) & (0xfu >> up) & 0xfu;
+        const int sk = skip - c0;
+        if (sk >= 0 && sk <= 3) m &= ~(1u << sk);
+        return m;
     };
-    uint32_t xw[U], yw[U], pw[4];
-    auto run_load = [&](int first, int c1, int skip, uint32_t mul, int sft, uint32_t base, uint32_t *w) {
+    uint32_t xw[UT][4], pw[4], ym[UT];
+    uint4 yw[UT];
+    auto tiles_load = [&](int tx, int ty) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int c = first + lane + u * G;
-            w[u] = (c <= c1 && c != skip) ? K[run_idx(c, mul, sft, base)] : 0xffffffffu;   // all ones: nothing to mark
+        for (int u = 0; u < UT; u++) {
+            const int Tx = tx + lane + u * G, Ty = ty + lane + u * G;
+            const uint32_t mxm = Tx <= xt1 ? tile_mask(Tx, fx0, fx1, x) : 0u, mym = Ty <= yt1 ? tile_mask(Ty, fy0, fy1, y) : 0u;
+            const uint32_t bx = xbase + (uint32_t)Tx * xmul, by = ybase + (uint32_t)Ty * ymul;
+#pragma unroll
+            for (int j = 0; j < 4; j++) xw[u][j] = ((mxm >> j) & 1u) ? K[bx + 4 * j] : 0xffffffffu;
+            // (nothing may consume the loaded words here: a use right behind its load would stall the issue of the next)
+            ym[u] = mym;
+            yw[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            if (mym) yw[u] = *reinterpret_cast<const uint4 *>(K + by);
         }
     };
-    auto run_store = [&](int first, uint32_t mul, int sft, uint32_t base, const uint32_t *w) {
+    auto tiles_store = [&](int tx, int ty) {
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            if (((w[u] >> zsh) & 31u) == 0u) K[run_idx(first + lane + u * G, mul, sft, base)] = w[u] | (kCodeSeen << zsh);
+        for (int u = 0; u < UT; u++) {
+            const uint32_t bx = xbase + (uint32_t)(tx + lane + u * G) * xmul, by = ybase + (uint32_t)(ty + lane + u * G) * ymul;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (((xw[u][j] >> zsh) & 31u) == 0u) K[bx + 4 * j] = xw[u][j] | (kCodeSeen << zsh);
+            const uint32_t yv[4] = {yw[u].x, yw[u].y, yw[u].z, yw[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (((ym[u] >> j) & 1u) && ((yv[j] >> zsh) & 31u) == 0u) K[by + j] = yv[j] | (kCodeSeen << zsh);
+        }
     };
-    run_load(fx0, fx1, x, xmul, 2, xbase, xw);
-    run_load(fy0, fy1, y, ymul, 0, ybase, yw);
+    tiles_load(xt0, yt0);
     const bool pon[4] = {wxh, wxl, wyh, wyl};
     const uint32_t pidx[4] = {k_xpart(R, r.x1 + kPadLo) + xbase, k_xpart(R, r.x0 + kPadLo) + xbase,
                               k_ypart(R, r.y1 + kPadLo) + ybase, k_ypart(R, r.y0 + kPadLo) + ybase};
@@ -531,17 +555,14 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
 #pragma unroll
         for (int b = 0; b < 3; b++) if (b < nzb && persist && cw[b] != cw_old[b]) K[cbase + ((uint32_t)b << 4)] = cw[b];
     }
-    run_store(fx0, xmul, 2, xbase, xw);
-    run_store(fy0, ymul, 0, ybase, yw);
+    tiles_store(xt0, yt0);
 #pragma unroll
     for (int d = 0; d < 4; d++)
         if (((pw[d] >> zsh) & 31u) == 0u) K[pidx[d]] = pw[d] | (kCodeWall << zsh);
     // the rest of long runs, both runs per round so that their loads share one latency
-    for (int k = G * U; fx0 + k <= fx1 || fy0 + k <= fy1; k += G * U) {
-        run_load(fx0 + k, fx1, x, xmul, 2, xbase, xw);
-        run_load(fy0 + k, fy1, y, ymul, 0, ybase, yw);
-        run_store(fx0 + k, xmul, 2, xbase, xw);
-        run_store(fy0 + k, ymul, 0, ybase, yw);
+    for (int k = G * UT; xt0 + k <= xt1 || yt0 + k <= yt1; k += G * UT) {
+        tiles_load(xt0 + k, yt0 + k);
+        tiles_store(xt0 + k, yt0 + k);
     }
 
     // ---- 3. the window: clip to [-2, 20], (m + 2) / 22 (:273-275), one float4 per column; neighbour codes

@@ -56,5 +56,5 @@ def text(f, l):
     s = srcs[f]
     return s[l - 1].strip()[:110] if 0 < l <= len(s) else ""
 tot_s = sum(samples.values()) or 1
-for (f, l), n in sorted(per_line.items(), key=lambda kv: -kv[1])[:top]:
+for (f, l), n in sorted(per_line.items(), key=(lambda kv: -samples[kv[0]]) if os.environ.get("NAV3D_SORT") == "samples" else (lambda kv: -kv[1]))[:top]:
     print(f"{n / n_envs:7.2f}  {100 * samples[(f, l)] / tot_s:5.1f}%smp  {f}:{l:<5} {text(f, l)}")
