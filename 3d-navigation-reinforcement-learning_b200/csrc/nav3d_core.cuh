@@ -491,14 +491,23 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
     constexpr int UT = G >= 4 ? 1 : (G == 2 ? 2 : 3);
     const int xt0 = (fx0 + kPadLo) >> 2, xt1 = fx1 >= fx0 ? (fx1 + kPadLo) >> 2 : xt0 - 1;
     const int yt0 = (fy0 + kPadLo) >> 2, yt1 = fy1 >= fy0 ? (fy1 + kPadLo) >> 2 : yt0 - 1;
-    // bit j: cell 4T - pad + j of tile T lies in [c_lo, c_hi] and is not the centre
-    auto tile_mask = [&](int T, int c_lo, int c_hi, int skip) {
-        const int c0 = 4 * T - kPadLo;
-        const int lo_ = imin(imax(c_lo - c0, 0), 4), up = imin(imax(c0 + 3 - c_hi, 0), 4);
-        uint32_t m = (0xfu << lo_) & (0xfu >> up) & 0xfu;
-        const int sk = skip - c0;
-        if (sk >= 0 && sk <= 3) m &= ~(1u << sk);
+    // bit c + pad of a run mask: cell c of the run is to be marked (free range, centre column excluded); a tile's four
+    // cells are then four consecutive bits (bordered coordinates < 64 + pad + 1 fit 64 + 3 bits: rooms are at most 64 wide,
+    // so the mask is kept as 64 bits of cells 0 .. 63 - pad and the top cells are handled by the clamp below)
+    auto run_mask = [&](int c_lo, int c_hi, int skip) {
+        unsigned long long m = 0ull;
+        if (c_hi >= c_lo) {
+            const int n = c_hi - c_lo + 1;                           // 1 .. 64
+            m = (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) << c_lo;    // bit c: cell c (c_lo >= 0)
+            m &= ~(1ull << skip);
+        }
         return m;
+    };
+    const unsigned long long xrm = run_mask(fx0, fx1, x), yrm = run_mask(fy0, fy1, y);
+    // the four cells 4T - pad .. 4T - pad + 3 of tile T
+    auto tile_mask = [&](unsigned long long rm, int T) {
+        const int c0 = 4 * T - kPadLo;                               // >= -pad
+        return (uint32_t)(c0 >= 0 ? (rm >> c0) : (rm << (-c0))) & 0xfu;
     };
     uint32_t xw[UT][4], pw[4], ym[UT];
     uint4 yw[UT];
@@ -506,7 +515,7 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
 #pragma unroll
         for (int u = 0; u < UT; u++) {
             const int Tx = tx + lane + u * G, Ty = ty + lane + u * G;
-            const uint32_t mxm = Tx <= xt1 ? tile_mask(Tx, fx0, fx1, x) : 0u, mym = Ty <= yt1 ? tile_mask(Ty, fy0, fy1, y) : 0u;
+            const uint32_t mxm = Tx <= xt1 ? tile_mask(xrm, Tx) : 0u, mym = Ty <= yt1 ? tile_mask(yrm, Ty) : 0u;
             const uint32_t bx = xbase + (uint32_t)Tx * xmul, by = ybase + (uint32_t)Ty * ymul;
 #pragma unroll
             for (int j = 0; j < 4; j++) xw[u][j] = ((mxm >> j) & 1u) ? K[bx + 4 * j] : 0xffffffffu;

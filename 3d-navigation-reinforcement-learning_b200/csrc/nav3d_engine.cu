@@ -571,9 +571,9 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
         return fail(NAV3D_ERR_INVALID, "env_kind must be NAV3D_ENV_CUBIC or NAV3D_ENV_SIMPLE");
     if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
-    // Defaults from the sweeps in DESIGN.md §6: CubicEnv 4 lanes per env at 64 registers (__launch_bounds__(128, 8));
-    // simpleEnv (6L ray cells, no window) 2 lanes per env.
-    int G = cfg->lanes_per_env == 0 ? (cfg->env_kind == NAV3D_ENV_SIMPLE ? 2 : 4) : cfg->lanes_per_env;
+    // Defaults from the sweeps in DESIGN.md §6: CubicEnv one thread per env (the step_tpe / rollout_tpe kernels, 3 CTAs of
+    // 128 threads per SM with every register the step wants); simpleEnv (6L ray cells, no window) 2 lanes per env.
+    int G = cfg->lanes_per_env == 0 ? (cfg->env_kind == NAV3D_ENV_SIMPLE ? 2 : 1) : cfg->lanes_per_env;
     if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
         return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
     int ndev = 0;
@@ -584,8 +584,8 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     if (!e) return fail(NAV3D_ERR_NOMEM, "out of host memory");
     e->cfg = *cfg;
     e->G = G;
-    e->minb = 8;
-    if (const char *mb = getenv("NAV3D_MINB")) e->minb = atoi(mb);
+    e->minb = (cfg->env_kind == NAV3D_ENV_SIMPLE || G > 1) ? 8 : 3;
+    if (const char *mb = getenv("NAV3D_MINB")) { if (atoi(mb) > 0) e->minb = atoi(mb); }   // tuning knob (tools/*sweep.sh)
     if (const char *pd = getenv("NAV3D_PDL")) e->pdl = atoi(pd) != 0;
     const size_t N = (size_t)cfg->n_envs;
     cudaError_t err = cudaSuccess;
@@ -850,24 +850,15 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
         if (G == 1) {                                  // thread per env: staged, coalesced observation stores
             static const bool staged = !(getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) == 0);
             switch (minb * 2 + (staged ? 1 : 0)) {
+                case 8: cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, false>, e->P, io); break;
+                case 9: cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, true>, e->P, io); break;
                 case 6: cudaLaunchKernelEx(&cfg, step_tpe_kernel<3, false>, e->P, io); break;
-                case 7: cudaLaunchKernelEx(&cfg, step_tpe_kernel<3, true>, e->P, io); break;
-                case 10: cudaLaunchKernelEx(&cfg, step_tpe_kernel<5, false>, e->P, io); break;
-                case 11: cudaLaunchKernelEx(&cfg, step_tpe_kernel<5, true>, e->P, io); break;
-                case 12: cudaLaunchKernelEx(&cfg, step_tpe_kernel<6, false>, e->P, io); break;
-                case 13: cudaLaunchKernelEx(&cfg, step_tpe_kernel<6, true>, e->P, io); break;
-                default:
-                    if (staged) cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, true>, e->P, io);
-                    else cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, false>, e->P, io);
+                default: cudaLaunchKernelEx(&cfg, step_tpe_kernel<3, true>, e->P, io); break;
             }
             return NAV3D_OK;
         }
-        switch (minb) {
-            case 6: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 6>, e->P, io); break;
-            case 3: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 3>, e->P, io); break;
-            case 4: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 4>, e->P, io); break;
-            default: cudaLaunchKernelEx(&cfg, step_call_kernel<G, 8>, e->P, io); break;
-        }
+        if (minb == 6) cudaLaunchKernelEx(&cfg, step_call_kernel<G, 6>, e->P, io);
+        else cudaLaunchKernelEx(&cfg, step_call_kernel<G, 8>, e->P, io);
         return NAV3D_OK;
     });
     if (rc) return rc;
@@ -949,37 +940,13 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
     cudaStream_t s = (cudaStream_t)stream;
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
-        // tuning knobs: NAV3D_ROLLOUT_MINB = register budget, NAV3D_ROLLOUT_SMEM = dynamic shared memory per CTA (limits the
-        // resident CTAs per SM and with them the envs whose knowledge lines compete for L2)
-        static const int rminb = getenv("NAV3D_ROLLOUT_MINB") ? atoi(getenv("NAV3D_ROLLOUT_MINB")) : 6;
-        static const int rsmem = getenv("NAV3D_ROLLOUT_SMEM") ? atoi(getenv("NAV3D_ROLLOUT_SMEM")) : 0;
-        auto launch = [&](auto kern) {
-            if (rsmem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rsmem);
-            kern<<<grid_for(e->cfg.n_envs, G), kBlock, rsmem, s>>>(e->P, T, t0, obs, obs_last, reward, done, actions_out,
-                                                                    e->d_reward, e->d_term, e->d_trunc);
-        };
         if (G == 1) {
-            auto launch1 = [&](auto kern) {
-                if (rsmem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rsmem);
-                kern<<<grid_for(e->cfg.n_envs, 1), kBlock, rsmem, s>>>(e->P, T, t0, obs, obs_last, reward, done, actions_out);
-            };
-            static const bool staged = getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) != 0;
-            switch (rminb * 2 + (staged ? 1 : 0)) {
-                case 6: launch1(rollout_tpe_kernel<3, false>); break;
-                case 7: launch1(rollout_tpe_kernel<3, true>); break;
-                case 10: launch1(rollout_tpe_kernel<5, false>); break;
-                case 11: launch1(rollout_tpe_kernel<5, true>); break;
-                case 12: launch1(rollout_tpe_kernel<6, false>); break;
-                case 13: launch1(rollout_tpe_kernel<6, true>); break;
-                default:
-                    if (staged) launch1(rollout_tpe_kernel<4, true>);
-                    else launch1(rollout_tpe_kernel<4, false>);
-            }
+            rollout_tpe_kernel<3, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward, done,
+                                                                                   actions_out);
             return NAV3D_OK;
         }
-        if (rminb == 3) launch(rollout_kernel<G, 3>);
-        else if (rminb == 4) launch(rollout_kernel<G, 4>);
-        else launch(rollout_kernel<G, 6>);
+        rollout_kernel<G, 6><<<grid_for(e->cfg.n_envs, G), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward, done, actions_out,
+                                                                           e->d_reward, e->d_term, e->d_trunc);
         return NAV3D_OK;
     });
     if (rc) return rc;

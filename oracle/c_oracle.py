@@ -48,6 +48,7 @@ def lib():
         "orc_vec_reset": (None, [P, P, P]), "orc_vec_set_ids": (None, [P, P]), "orc_vec_state": (None, [P, P]),
         "orc_vec_step": (None, [P, P, P, P, P, P, P, P, P, P, P]),
         "orc_vec_rollout_random": (C.c_long, [P, I, C.c_uint32, P, P]),
+        "orc_vec_rollout_random_obs": (C.c_long, [P, I, C.c_uint32, P]),
         "orc_set_threads": (None, [I]), "orc_get_threads": (I, []), "orc_hw_threads": (I, []),
     }
     for name, (res, args) in sig.items():
@@ -278,6 +279,11 @@ class OracleVec:
         rs, dc = C.c_double(), C.c_long()
         n = lib().orc_vec_rollout_random(self.h, T, t0, C.byref(rs), C.byref(dc))
         return n, rs.value, dc.value
+
+    def rollout_random_obs(self, T: int, t0: int = 0) -> np.ndarray:
+        """T random-action steps like ``rollout_random``; ``self.obs`` holds the observation after the last one."""
+        lib().orc_vec_rollout_random_obs(self.h, T, t0, _p(self.obs))
+        return self.obs
 
     def state(self) -> np.ndarray:
         """int64 [n, 15]: CUBIC_STATE columns + room index + episode number."""

@@ -27,9 +27,27 @@ struct Emu {
     bool descending = false;
 };
 
+// Address-sanitizer build (tools/emu_asan.sh; compute-sanitizer is not available on the GPU pool): an env may only touch
+// the part of its knowledge block that its CURRENT room owns — the K bricks of that room and the overflow bytes of its cells;
+// everything else of the block (sized for the largest room of the set) is poisoned, so that an index computed from a wrong
+// room, a negative coordinate or a missing border shows up as an ASan report instead of silently landing in padding.
+#ifdef NAV3D_EMU_ASAN
+#include <sanitizer/asan_interface.h>
+static void fence_env(Emu *e, int env, uint32_t room) {
+    uint8_t *blk = e->know.data() + (size_t)env * e->P.env_stride;
+    const RoomDev &R = e->rooms[room];
+    ASAN_POISON_MEMORY_REGION(blk, e->P.env_stride);
+    ASAN_UNPOISON_MEMORY_REGION(blk, k_bytes(R));
+    ASAN_UNPOISON_MEMORY_REGION(blk + e->P.ovf_off, (size_t)R.W * R.D * R.H);
+}
+#else
+static void fence_env(Emu *, int, uint32_t) {}
+#endif
+
 template <int G> static void reset_one(Emu *e, int env, uint32_t room, uint32_t k, uint32_t ep_after, float *orow) {
     ResetCtx c;
     uint32_t nbr = 0;
+    fence_env(e, env, room);
     for (int lane = 0; lane < G; lane++) reset_clear<G>(e->P, env, lane, room);
     for (int i = 0; i < G; i++) {
         const int lane = e->descending ? G - 1 - i : i;
@@ -113,6 +131,9 @@ void *emu_create(int n_envs, int L, double crash, unsigned long long seed, unsig
     for (int c = 0; c <= L; c++) e->dist_lut.push_back((float)(std::nearbyint((double)c * cell_size * 100.0) / 100.0));
     e->states.assign((size_t)n_envs, EnvState{});
     e->know.assign(stride * (size_t)n_envs, 0xAB);     // poison: a reset must clear what it uses
+#ifdef NAV3D_EMU_ASAN
+    if (!e->simple) ASAN_POISON_MEMORY_REGION(e->know.data(), e->know.size());   // nothing is owned before the first reset
+#endif
     for (int i = 0; i < kLutSize; i++) e->lut[i] = 0.f;
     for (int i = 0; i < 32; i++) {
         const int v = i == 0 ? -1 : (i == 1 ? -2 : std::min(i - 2, 20));
@@ -128,7 +149,19 @@ void *emu_create(int n_envs, int L, double crash, unsigned long long seed, unsig
     P.dist_lut = e->dist_lut.data(); P.obs_dim = e->simple ? 6 * L + 7 : kObsDim;
     return e;
 }
-void emu_destroy(void *h) { delete (Emu *)h; }
+void emu_destroy(void *h) {
+#ifdef NAV3D_EMU_ASAN
+    ASAN_UNPOISON_MEMORY_REGION(((Emu *)h)->know.data(), ((Emu *)h)->know.size());
+#endif
+    delete (Emu *)h;
+}
+// negative control of the sanitizer build: reads the byte at `offset` of an env's knowledge block (outside the fence -> report)
+int emu_probe(void *h, int env, long offset) {
+    Emu *e = (Emu *)h;
+    const volatile uint8_t *p = e->know.data() + (size_t)env * e->P.env_stride + offset;
+    return *p;
+}
+long emu_owned_k_bytes(void *h, int env) { Emu *e = (Emu *)h; return (long)k_bytes(e->rooms[e->states[env].room]); }
 int emu_room_n_free(void *h, int r) { return (int)((Emu *)h)->rooms[r].n_free; }
 
 void emu_reset(void *h, const int *env_ids, int n, const int *picks, float *obs) {

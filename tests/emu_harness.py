@@ -6,19 +6,29 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 HERE = Path(__file__).resolve().parent / "emu"
-LIB = HERE / "libnav3d_emu.so"
+ASAN = os.environ.get("NAV3D_EMU_ASAN") == "1"          # tools/emu_asan.sh: the same source under AddressSanitizer + UBSan
+LIB = HERE / ("libnav3d_emu_asan.so" if ASAN else "libnav3d_emu.so")
 CORE = HERE.parent.parent / "3d-navigation-reinforcement-learning_b200" / "csrc" / "nav3d_core.cuh"
 _lib = None
+
+
+def build():
+    src = HERE / "nav3d_emu.cu"
+    if True:
+        if not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime, CORE.stat().st_mtime):
+            extra = (["-g", "-DNAV3D_EMU_ASAN", "-Xcompiler", "-fsanitize=address", "-Xcompiler", "-fsanitize=undefined", "-Xcompiler",
+                      "-fno-omit-frame-pointer", "-Xcompiler", "-fno-sanitize-recover=undefined"] if ASAN else [])
+            subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-shared", "-Xcompiler",
+                                   "-fPIC", *extra, "-o", str(LIB), str(src)], stdout=subprocess.DEVNULL)
 
 
 def lib():
     global _lib
     if _lib is None:
-        src = HERE / "nav3d_emu.cu"
-        if not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime, CORE.stat().st_mtime):
-            subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-shared", "-Xcompiler",
-                                   "-fPIC", "-o", str(LIB), str(src)], stdout=subprocess.DEVNULL)
+        build()
         L = C.CDLL(str(LIB))
         P, I = C.c_void_p, C.c_int
         L.emu_create.restype = P

@@ -105,11 +105,14 @@ def test_sharding_independence(oracle):
     assert np.array_equal(whole.state()[:, :14], np.concatenate([h.state() for h in halves])[:, :14])
 
 
-def test_fused_random_rollout_matches_oracle(oracle):
+@pytest.mark.parametrize("n,T", [(1024, 1100), (1013, 550)])
+def test_fused_random_rollout_matches_oracle(oracle, n, T):
+    """nav3d_rollout_random with every observation, reward, done flag and action written: each of the T steps equals the
+    oracle's, auto-resets included (1013 envs: the last warp of the thread-per-env kernel is ragged)."""
     import torch
     from nav3d import Engine
     rooms = load_room_dir(ROOMS / "P1_training", sort=True)
-    n, T, seed = 1024, 1100, 17
+    seed = 17
     orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
     ov = oracle.OracleVec(n, orooms, 10, -2.0, seed, 100, True)
     oracle.set_threads(oracle.hw_threads())
@@ -196,6 +199,36 @@ def test_full_size_sample_against_oracle(oracle):
     assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
 
 
+def test_fused_full_observation_rollout_full_size(oracle):
+    """What bench.py reports as extra.fused_rollout_full: nav3d_rollout_random at 2^20 envs, T = 32, ALL observations
+    written ([32, 2^20, 80] f32).  Two launches back to back; a strided sample of 512 envs is replayed by the oracle and
+    every one of the 64 steps compared (observation bits, f32 reward, done), then the final state."""
+    import torch
+    from nav3d import Engine
+    rooms = load_room_dir(ROOMS / "P1_training", sort=True)
+    n, T, seed = 1 << 20, 32, 77
+    eng = Engine(n, rooms, local_map_length=10, seed=seed)
+    eng.reset()
+    ids = np.arange(11, n, n // 512, dtype=np.uint32)
+    orooms = [oracle.OracleRoom(r.grid, -2) for r in rooms]
+    ov = oracle.OracleVec(len(ids), orooms, 10, -2.0, seed, 0, True)
+    ov.set_ids(ids)
+    ov.reset()
+    tid = torch.as_tensor(ids.astype(np.int64), device=eng.device)
+    obs = torch.zeros((T, n, 80), dtype=torch.float32, device=eng.device)
+    rew = torch.zeros((T, n), dtype=torch.float32, device=eng.device)
+    done = torch.zeros((T, n), dtype=torch.uint8, device=eng.device)
+    for launch in range(2):
+        eng.rollout_random(T, launch * T, obs=obs, reward=rew, done=done)
+        o, r, d = obs[:, tid].cpu().numpy(), rew[:, tid].cpu().numpy(), done[:, tid].cpu().numpy()
+        for t in range(T):
+            ov.step(np.array([oracle.action(seed, int(i), launch * T + t) for i in ids]))
+            assert np.array_equal(o[t].view(np.uint32), ov.obs.view(np.uint32)), f"obs launch {launch} t={t}"
+            assert np.array_equal(r[t], ov.reward.astype(np.float32)) and np.array_equal(d[t], ov.terminated | ov.truncated)
+        assert bool(((obs >= 0) & (obs <= 1)).all()) and bool((obs[:, :, 73:] == 0).all())
+    assert np.array_equal(eng.get_state()[tid].cpu().numpy()[:, :15].astype(np.int64), ov.state())
+
+
 def test_config3_full_size_sample_against_oracle(oracle):
     """BASELINE.json configs[2] at its full size: 65 536 envs over the 42 P2+P3 training rooms (heterogeneous sizes, per-env
     room index), stepped one launch per step with host-chosen random actions; a strided sample of 512 envs is replayed by
@@ -236,14 +269,16 @@ def test_config3_full_size_sample_against_oracle(oracle):
     assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
 
 
-@pytest.mark.parametrize("minb", ["6", "8", "10", "12"])
-def test_occupancy_variants(oracle, monkeypatch, minb):
-    """The register-capped instantiations of the step kernel (__launch_bounds__ min CTAs per SM, NAV3D_MINB) must give the
-    same bits, auto-reset (an out-of-line device call at the end of the step) included."""
+@pytest.mark.parametrize("lanes,minb,staged", [(1, "3", "1"), (1, "3", "0"), (1, "4", "1"), (1, "4", "0"), (4, "6", "1"), (4, "8", "1")])
+def test_kernel_variants(oracle, monkeypatch, lanes, minb, staged):
+    """The instantiations of the step kernel behind the tuning knobs — register budget (__launch_bounds__ min CTAs per SM,
+    NAV3D_MINB), staged or direct observation stores of the thread-per-env kernel (NAV3D_TPE_STAGED), lanes per env — must
+    give the same bits, auto-reset (an out-of-line device call at the end of the step) included."""
     monkeypatch.setenv("NAV3D_MINB", minb)
+    monkeypatch.setenv("NAV3D_TPE_STAGED", staged)
     rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt"), load_room_file(ROOMS / "P2_training" / "tightcorridor.txt"),
              load_room_file(ROOMS / "P1_training" / "Empty_room_3mx3mx3m_0.25m_cellsize.txt")]
-    n_done = lockstep(oracle, rooms, n=1500, L=10, steps=650, seed=21, lanes=4, state_every=50)
+    n_done = lockstep(oracle, rooms, n=1500, L=10, steps=650, seed=21, lanes=lanes, state_every=50)
     assert n_done > 1500
 
 

@@ -58,3 +58,15 @@ def text(f, l):
 tot_s = sum(samples.values()) or 1
 for (f, l), n in sorted(per_line.items(), key=(lambda kv: -samples[kv[0]]) if os.environ.get("NAV3D_SORT") == "samples" else (lambda kv: -kv[1]))[:top]:
     print(f"{n / n_envs:7.2f}  {100 * samples[(f, l)] / tot_s:5.1f}%smp  {f}:{l:<5} {text(f, l)}")
+# optional: totals per named line range of nav3d_core.cuh (env NAV3D_RANGES="name:lo-hi,...")
+rng = os.environ.get("NAV3D_RANGES")
+if rng:
+    print("-- by range (warp-instructions per env-step, share of stall samples)")
+    for part in rng.split(","):
+        name, lh = part.split(":"); lo, hi = (int(v) for v in lh.split("-"))
+        n = sum(v for (f, l), v in per_line.items() if f == "nav3d_core.cuh" and lo <= l <= hi)
+        sm = sum(v for (f, l), v in samples.items() if f == "nav3d_core.cuh" and lo <= l <= hi)
+        print(f"{n / n_envs:7.2f}  {100 * sm / tot_s:5.1f}%smp  {name}")
+    n = sum(v for (f, l), v in per_line.items() if f != "nav3d_core.cuh")
+    sm = sum(v for (f, l), v in samples.items() if f != "nav3d_core.cuh")
+    print(f"{n / n_envs:7.2f}  {100 * sm / tot_s:5.1f}%smp  (other files)")
