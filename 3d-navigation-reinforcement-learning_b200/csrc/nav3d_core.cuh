@@ -987,9 +987,12 @@ NAV3D_HD void simple_reset_env_philox(const EngineParams &P, int env, int lane, 
     simple_reset_env<G>(P, env, lane, lane_in_warp, room, mulhi_range(u[1], nf), mulhi_range(u[2], nf), episode + 1u, obs_row);
 }
 
-template <int G>
-NAV3D_HD void simple_step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
-                              long long row) {
+// STAGED (G == 1, the thread-per-env kernel): the 6L+7 floats go to `stage_row` (shared memory), `*dst_slot` receives the
+// global row they belong to (NULL = none), and the auto-reset is left to the caller (returns true when it is due), which
+// runs it after the warp has written the staged rows out.
+template <int G, bool STAGED = false>
+NAV3D_HD bool simple_step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
+                              long long row, float *stage_row = nullptr, float **dst_slot = nullptr) {
     const EnvState st = P.states[env];
     const RoomDev R = P.rooms[st.room];
     uint32_t *K = reinterpret_cast<uint32_t *>(P.know + (unsigned long long)env * P.env_stride);
@@ -1026,6 +1029,7 @@ NAV3D_HD void simple_step_env(const EngineParams &P, const StepIO &io, int env, 
     const bool will_reset = P.auto_reset && (done || truncated);
     float *orow = io.obs + row * P.obs_dim;
     if (will_reset) orow = io.terminal_obs ? io.terminal_obs + row * P.obs_dim : nullptr;
+    if (STAGED) { *dst_slot = orow; if (orow) orow = stage_row; }
     if (!will_reset || orow)
         simple_observe<G>(P, R, K, lane, lane_in_warp, x, y, z, facing, centre_mem, centre, a, orow);
     if (lane == 0) {
@@ -1057,10 +1061,11 @@ NAV3D_HD void simple_step_env(const EngineParams &P, const StepIO &io, int env, 
             P.states[env] = ns;
         }
     }
-    if (will_reset) {
+    if (will_reset && !STAGED) {
         group_sync<G>(lane_in_warp);
         simple_reset_env_philox<G>(P, env, lane, lane_in_warp, st.episode, io.obs + row * P.obs_dim);
     }
+    return will_reset;
 }
 
 }  // namespace nav3d

@@ -36,12 +36,13 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 __device__ __forceinline__ void fill_lut(float *lut, int L) {
     // nav3d_core.cuh kLut*: observation value of a knowledge code = (clip(v, -2, 20) + 2) / 22 (CubicEnv.py:273-275),
     // k / 5 (:284), d / L (:287); correctly rounded f32 quotients like NumPy's
-    const int t = threadIdx.x;
-    if (t < 32) {
-        const int v = t == 0 ? -1 : (t == 1 ? -2 : min(t - 2, 20));
-        lut[t] = __fdiv_rn((float)(v + 2), 22.0f);
-    } else if (t >= kLutFifth && t < kLutFifth + 6) lut[t] = __fdiv_rn((float)(t - kLutFifth), 5.0f);
-    else if (t >= kLutDown && t < kLutSize) lut[t] = __fdiv_rn((float)(t - kLutDown), (float)L);
+    for (int t = threadIdx.x; t < kLutSize; t += blockDim.x) {
+        if (t < 32) {
+            const int v = t == 0 ? -1 : (t == 1 ? -2 : min(t - 2, 20));
+            lut[t] = __fdiv_rn((float)(v + 2), 22.0f);
+        } else if (t >= kLutFifth && t < kLutFifth + 6) lut[t] = __fdiv_rn((float)(t - kLutFifth), 5.0f);
+        else if (t >= kLutDown && t < kLutSize) lut[t] = __fdiv_rn((float)(t - kLutDown), (float)L);
+    }
     __syncthreads();
 }
 
@@ -225,18 +226,18 @@ __device__ __noinline__ void tpe_reset(const EngineParams &P, bool mine, uint32_
     if (STAGED) flush_rows(stage, dst, lane);
 }
 
-template <int MINB, bool STAGED>
-__global__ void __launch_bounds__(kBlock, MINB) step_tpe_kernel(const __grid_constant__ EngineParams P, StepIO io) {
+template <int BLOCK, bool STAGED>
+__device__ __forceinline__ void step_tpe_body(const EngineParams &P, const StepIO &io) {
     __shared__ float lut[kLutSize];
-    __shared__ __align__(16) float stage_all[STAGED ? kBlock * kStageStride : 4];
-    __shared__ float *dst_all[STAGED ? kBlock : 1];
+    __shared__ __align__(16) float stage_all[STAGED ? BLOCK * kStageStride : 4];
+    __shared__ float *dst_all[STAGED ? BLOCK : 1];
     asm volatile("griddepcontrol.launch_dependents;");          // programmatic dependent launch, as in step_call_kernel
     fill_lut(lut, P.L);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
     float *stage = stage_all + wbase * kStageStride;
     float **dst = dst_all + wbase;
-    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (gid - lane >= io.env_n) return;                          // the whole warp is past the range
     const bool valid = gid < io.env_n;
     const long long env = io.env0 + gid;
@@ -250,6 +251,15 @@ __global__ void __launch_bounds__(kBlock, MINB) step_tpe_kernel(const __grid_con
         const uint32_t episode = rst ? P.states[env].episode : 0u;   // untouched by a step that ends its episode
         tpe_reset<STAGED>(P, rst, (uint32_t)env, episode, false, 0u, 0u, lut, io.obs, stage, dst, lane);
     }
+}
+template <int BLOCK, int MINB, bool STAGED>
+__global__ void __launch_bounds__(BLOCK, MINB) step_tpe_kernel(const __grid_constant__ EngineParams P, StepIO io) {
+    step_tpe_body<BLOCK, STAGED>(P, io);
+}
+// 64-thread CTAs capped at 144 registers: 14 warps per SM instead of 12 (7 CTAs), which also divides the 131 072-, 262 144-
+// and 524 288-env shards of the multi-GPU job into whole waves (27.7 / 55.4 / 110.7 warps per SM: 2 / 4 / 8 waves of 14)
+__global__ void __maxnreg__(144) step_tpe144_kernel(const __grid_constant__ EngineParams P, StepIO io) {
+    step_tpe_body<64, true>(P, io);
 }
 
 __global__ void __launch_bounds__(kBlock) reset_tpe_kernel(const __grid_constant__ EngineParams P,
@@ -282,18 +292,17 @@ __global__ void __launch_bounds__(kBlock) reset_tpe_kernel(const __grid_constant
 // T fused steps per env, thread per env (on-device Philox actions).  The record stays in the
 // thread's registers for the whole rollout and the knowledge lines it touches stay in L2, so DRAM sees the outputs the
 // caller asked for plus one pass over the touched lines.
-template <int MINB, bool STAGED>
-__global__ void __launch_bounds__(kBlock, MINB) rollout_tpe_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0,
-                                                                   float *obs, float *obs_last, float *reward, uint8_t *done,
-                                                                   uint8_t *actions_out) {
+template <int BLOCK, bool STAGED>
+__device__ __forceinline__ void rollout_tpe_body(const EngineParams &P, int T, uint32_t t0, float *obs, float *obs_last,
+                                                 float *reward, uint8_t *done, uint8_t *actions_out) {
     __shared__ float lut[kLutSize];
-    __shared__ __align__(16) float stage_all[STAGED ? kBlock * kStageStride : 4];
-    __shared__ float *dst_all[STAGED ? kBlock : 1];
+    __shared__ __align__(16) float stage_all[STAGED ? BLOCK * kStageStride : 4];
+    __shared__ float *dst_all[STAGED ? BLOCK : 1];
     fill_lut(lut, P.L);
     const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
     float *stage = stage_all + wbase * kStageStride;
     float **dst = dst_all + wbase;
-    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     const long long N = P.n_envs;
     if (gid - lane >= N) return;
     const bool valid = gid < N;
@@ -327,6 +336,16 @@ __global__ void __launch_bounds__(kBlock, MINB) rollout_tpe_kernel(const __grid_
         }
     }
     if (valid) P.states[env] = st;
+}
+template <int BLOCK, int MINB, bool STAGED>
+__global__ void __launch_bounds__(BLOCK, MINB) rollout_tpe_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0,
+                                                                  float *obs, float *obs_last, float *reward, uint8_t *done,
+                                                                  uint8_t *actions_out) {
+    rollout_tpe_body<BLOCK, STAGED>(P, T, t0, obs, obs_last, reward, done, actions_out);
+}
+__global__ void __maxnreg__(144) rollout_tpe144_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0, float *obs,
+                                                       float *obs_last, float *reward, uint8_t *done, uint8_t *actions_out) {
+    rollout_tpe_body<64, true>(P, T, t0, obs, obs_last, reward, done, actions_out);
 }
 
 // T fused steps per env with on-device Philox actions.  An env's record and the knowledge lines it
@@ -396,6 +415,49 @@ __global__ void __launch_bounds__(kBlock) simple_reset_kernel(EngineParams P, co
         simple_reset_env<G>(P, env, lane, liw, room, k, kg, episode + 1u, orow);
     } else {
         simple_reset_env_philox<G>(P, env, lane, liw, episode, orow);
+    }
+}
+
+// simpleEnv, one thread per env: the 6L+7 floats of a row (124 B at L = 4: never 16-byte aligned, so a lane writing its own
+// row needs one 4-byte store per float) are assembled in shared memory and the warp writes its 32 rows — contiguous in the
+// caller's [N, 6L+7] array — with coalesced 128-byte store instructions.  Dynamic shared memory: kBlock x stride floats.
+__device__ __forceinline__ void flush_rows_n(const float *stage, int stride, float *const *dst, int obs_dim, int lane) {
+    __syncwarp();
+    int e = 0, j = lane;
+    while (j >= obs_dim) { j -= obs_dim; e++; }
+    while (e < 32) {
+        float *d = dst[e];
+        if (d != nullptr) __stcs(d + j, stage[e * stride + j]);
+        j += 32;
+        while (j >= obs_dim) { j -= obs_dim; e++; }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kBlock, 6) simple_step_tpe_kernel(const __grid_constant__ EngineParams P, StepIO io, int stride) {
+    extern __shared__ float stage_dyn[];
+    __shared__ float *dst_all[kBlock];
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    float *stage = stage_dyn + wbase * stride;
+    float **dst = dst_all + wbase;
+    const long long gid = (long long)blockIdx.x * kBlock + threadIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (gid - lane >= io.env_n) return;
+    const bool valid = gid < io.env_n;
+    const long long env = io.env0 + gid;
+    dst[lane] = nullptr;
+    bool rst = false;
+    if (valid)
+        rst = simple_step_env<1, true>(P, io, (int)env, 0, lane, (int)io.actions[env], env, stage + lane * stride, dst + lane);
+    flush_rows_n(stage, stride, dst, P.obs_dim, lane);
+    if (__any_sync(0xffffffffu, rst)) {
+        dst[lane] = nullptr;
+        if (rst) {
+            dst[lane] = io.obs + env * P.obs_dim;
+            simple_reset_env_philox<1>(P, (int)env, 0, lane, P.states[env].episode, stage + lane * stride);
+        }
+        flush_rows_n(stage, stride, dst, P.obs_dim, lane);
     }
 }
 
@@ -488,6 +550,7 @@ struct nav3d_engine {
     long long *d_actions = nullptr;
     int minb = 0;               // __launch_bounds__ min CTAs/SM variant of the step kernel (tuning knob)
     bool simple = false;        // NAV3D_ENV_SIMPLE
+    int simple_stride = 0;      // simpleEnv, lanes_per_env == 1: floats per staged row (odd: conflict-free), 0 = not staged
     bool reset_seen = false;    // a nav3d_reset call has been made since the rooms were loaded
     bool pdl = true;            // programmatic dependent launch of the step kernel (NAV3D_PDL=0 switches it off)
     float *d_dist_lut = nullptr;
@@ -573,7 +636,8 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
     // Defaults from the sweeps in DESIGN.md §6: CubicEnv one thread per env (the step_tpe / rollout_tpe kernels, 3 CTAs of
     // 128 threads per SM with every register the step wants); simpleEnv (6L ray cells, no window) 2 lanes per env.
-    int G = cfg->lanes_per_env == 0 ? (cfg->env_kind == NAV3D_ENV_SIMPLE ? 2 : 1) : cfg->lanes_per_env;
+    const int simple_dim = 6 * cfg->local_map_length + 7;
+    int G = cfg->lanes_per_env == 0 ? ((cfg->env_kind == NAV3D_ENV_SIMPLE && simple_dim > 95) ? 2 : 1) : cfg->lanes_per_env;
     if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
         return fail(NAV3D_ERR_INVALID, "lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
     int ndev = 0;
@@ -606,6 +670,12 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     P.auto_reset = cfg->auto_reset ? 1 : 0;
     P.rw = reference_reward_params(cfg->crash_penalty);
     e->simple = cfg->env_kind == NAV3D_ENV_SIMPLE;
+    if (e->simple && G == 1 && simple_dim <= 95) {
+        e->simple_stride = simple_dim | 1;
+        if (getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) == 0) e->simple_stride = 0;
+        else cudaFuncSetAttribute(simple_step_tpe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kBlock * e->simple_stride * sizeof(float)));
+    }
     P.obs_dim = e->simple ? 6 * cfg->local_map_length + 7 : kObsDim;
     if (e->simple) {
         // distances of simpleEnv: round(count * cell_size, 2) (simpleEnv.py:337) then float32
@@ -843,17 +913,31 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
         attr[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = 1;
         if (e->simple) {
+            if (G == 1 && e->simple_stride > 0) {      // thread per env, staged rows (6L+7 <= 95 floats)
+                cfg.dynamicSmemBytes = (size_t)kBlock * e->simple_stride * sizeof(float);
+                cudaLaunchKernelEx(&cfg, simple_step_tpe_kernel, e->P, io, e->simple_stride);
+                return NAV3D_OK;
+            }
             if (minb == 6) cudaLaunchKernelEx(&cfg, simple_step_kernel<G, 6>, e->P, io);
             else cudaLaunchKernelEx(&cfg, simple_step_kernel<G, 8>, e->P, io);
             return NAV3D_OK;
         }
         if (G == 1) {                                  // thread per env: staged, coalesced observation stores
             static const bool staged = !(getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) == 0);
+            // 64-thread CTAs at 144 registers for shards below two full waves of the 128-thread kernel (measured: 65 536
+            // envs 24.6 -> 20.9 us per step; no gain from 131 072 envs on), NAV3D_TPE_BLOCK overrides
+            static const int tblock_env = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 0;
+            const int tblock = tblock_env ? tblock_env : (n <= 98304 ? 64 : 128);
+            if (tblock == 64) {
+                cfg.gridDim = dim3((unsigned)((n + 63) / 64)); cfg.blockDim = dim3(64);
+                cudaLaunchKernelEx(&cfg, step_tpe144_kernel, e->P, io);
+                return NAV3D_OK;
+            }
             switch (minb * 2 + (staged ? 1 : 0)) {
-                case 8: cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, false>, e->P, io); break;
-                case 9: cudaLaunchKernelEx(&cfg, step_tpe_kernel<4, true>, e->P, io); break;
-                case 6: cudaLaunchKernelEx(&cfg, step_tpe_kernel<3, false>, e->P, io); break;
-                default: cudaLaunchKernelEx(&cfg, step_tpe_kernel<3, true>, e->P, io); break;
+                case 8: cudaLaunchKernelEx(&cfg, step_tpe_kernel<128, 4, false>, e->P, io); break;
+                case 9: cudaLaunchKernelEx(&cfg, step_tpe_kernel<128, 4, true>, e->P, io); break;
+                case 6: cudaLaunchKernelEx(&cfg, step_tpe_kernel<128, 3, false>, e->P, io); break;
+                default: cudaLaunchKernelEx(&cfg, step_tpe_kernel<128, 3, true>, e->P, io); break;
             }
             return NAV3D_OK;
         }
@@ -941,8 +1025,14 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         if (G == 1) {
-            rollout_tpe_kernel<3, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward, done,
-                                                                                   actions_out);
+            static const int tblock_env = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 0;
+            const int tblock = tblock_env ? tblock_env : (e->cfg.n_envs <= 98304 ? 64 : 128);
+            if (tblock == 64)
+                rollout_tpe144_kernel<<<(unsigned)((e->cfg.n_envs + 63) / 64), 64, 0, s>>>(e->P, T, t0, obs, obs_last,
+                                                                                                  reward, done, actions_out);
+            else
+                rollout_tpe_kernel<128, 3, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward,
+                                                                                            done, actions_out);
             return NAV3D_OK;
         }
         rollout_kernel<G, 6><<<grid_for(e->cfg.n_envs, G), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward, done, actions_out,

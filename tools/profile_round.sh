@@ -25,8 +25,6 @@ for r in step_${TAG}_cold step_${TAG}_steady rollout_${TAG}_cold rollout_${TAG}_
   NAV3D_SORT=samples python tools/sass_lines.py $O/prof_$r.ncu-rep $K $N 40 > $O/${r}_stall_lines.txt 2>&1
   rm -f $O/prof_$r.ncu-rep
 done
-export PATH=$PATH:/usr/local/cuda/bin
-SCMD="python -m pytest tests/test_gpu_parity.py -x -q -k engine_limits_and_degenerate_rooms"
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 $SCMD > $O/sanitizer_memcheck_$TAG.txt 2>&1; echo "memcheck exit code $?" >> $O/sanitizer_memcheck_$TAG.txt
-timeout 1200 compute-sanitizer --tool initcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "engine_limits_and_degenerate_rooms and 1" > $O/sanitizer_initcheck_$TAG.txt 2>&1; echo "initcheck exit code $?" >> $O/sanitizer_initcheck_$TAG.txt
+# compute-sanitizer is closed on this GPU pool ("runs under it have left GPUs needing a reset"): the memory-safety evidence is
+# tools/emu_asan.sh (the device source under ASan + UBSan on the host), logged in profiles/sanitizer_r02.txt
 ls -la $O/*$TAG*
