@@ -900,40 +900,67 @@ NAV3D_HD void simple_observe(const EngineParams &P, const RoomDev &R, uint32_t *
     const uint32_t centre_new = (lo1 | block_z) | ((hi0 | block_z) << 16);
     // ray order :243: forward, left, right, backward, up, down.  Headings N=+y, E=+x, S=-y, W=-x; heading -> axis
     // direction index is the same nibble table the move uses (N -> 2, E -> 0, S -> 3, W -> 1).
+    // The four horizontal rays, CH ray cells per lane per round: every word of a round is loaded before any is used or
+    // stored (a load -> test -> store chain per cell would serialise one memory latency per cell).
+    constexpr int CH = 4;
+    int adir[4], ddx[4], ddy[4];
 #pragma unroll
-    for (int d = 0; d < 6; d++) {
-        int a, dx = 0, dy = 0, dz = 0;
-        if (d < 4) {
-            const int h = (facing + ((0x2130 >> (4 * d)) & 3)) & 3;              // fwd +0, left +3, right +1, back +2
-            a = (0x1302 >> (4 * h)) & 3;
-            dx = (h == 1) - (h == 3); dy = (h == 0) - (h == 2);
-        } else { a = d; dz = (d == 4) ? 1 : -1; }
-        const int nfree = (int)((nf6 >> (8 * a)) & 0xff);
-        const bool wall = (wall6 >> a) & 1u, blocked = (blk6 >> a) & 1u;
-        for (int s = 1 + lane; s <= L; s += G) {
-            float v = -1.0f;                                                  // padding (:334-335)
-            if (s <= nfree) {
-                const int cx = x + dx * s, cy = y + dy * s, cz = z + dz * s;
-                if (d >= 4) v = k2_value(k2_code(centre_seen, cz));
-                else {
-                    uint32_t *p = K + s_index(R, cx, cy);
-                    uint32_t w = *p, n = w;
-                    int code = k2_code(w, cz);
-                    if (code == 0) { code = 1; n |= 1u << cz; }               // -1 -> 0
-                    v = k2_value(code);
-                    if (s == nfree && blocked && !wall) n |= (1u << cz) | (1u << (16 + cz));   // then becomes 2
-                    if (n != w) *p = n;
-                }
-            } else if (s == nfree + 1 && blocked) {
-                v = 2.0f;
-                if (wall && d < 4) {
-                    const int cx = x + dx * s, cy = y + dy * s;
-                    uint32_t *p = K + s_index(R, cx, cy);
-                    uint32_t w = *p, n = w | (1u << z) | (1u << (16 + z));
-                    if (n != w) *p = n;
-                }
+    for (int d = 0; d < 4; d++) {
+        const int h = (facing + ((0x2130 >> (4 * d)) & 3)) & 3;                  // fwd +0, left +3, right +1, back +2
+        adir[d] = (0x1302 >> (4 * h)) & 3;
+        ddx[d] = (h == 1) - (h == 3); ddy[d] = (h == 0) - (h == 2);
+    }
+    for (int s0 = 1; s0 <= L; s0 += CH * G) {
+        uint32_t w[4][CH];
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int nfree = (int)((nf6 >> (8 * adir[d])) & 0xff);
+            const bool wall = (wall6 >> adir[d]) & 1u, blocked = (blk6 >> adir[d]) & 1u;
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                const int sN = s0 + lane + u * G;
+                const bool need = sN <= L && (sN <= nfree || (sN == nfree + 1 && blocked && wall));
+                w[d][u] = need ? K[s_index(R, x + ddx[d] * sN, y + ddy[d] * sN)] : 0u;
             }
-            if (obs_row) obs_row[d * L + s - 1] = v;
+        }
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int nfree = (int)((nf6 >> (8 * adir[d])) & 0xff);
+            const bool wall = (wall6 >> adir[d]) & 1u, blocked = (blk6 >> adir[d]) & 1u;
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                const int sN = s0 + lane + u * G;
+                if (sN > L) continue;
+                float v = -1.0f;                                              // padding (:334-335)
+                const uint32_t old = w[d][u];
+                uint32_t n = old;
+                bool touch = false;
+                if (sN <= nfree) {
+                    int code = k2_code(old, z);
+                    if (code == 0) { code = 1; n |= 1u << z; }                // -1 -> 0
+                    v = k2_value(code);
+                    if (sN == nfree && blocked && !wall) n |= (1u << z) | (1u << (16 + z));   // then becomes 2
+                    touch = true;
+                } else if (sN == nfree + 1 && blocked) {
+                    v = 2.0f;
+                    if (wall) { n = old | (1u << z) | (1u << (16 + z)); touch = true; }
+                }
+                if (touch && n != old) K[s_index(R, x + ddx[d] * sN, y + ddy[d] * sN)] = n;
+                if (obs_row) obs_row[d * L + sN - 1] = v;
+            }
+        }
+    }
+    // the two vertical rays: all of their cells are in the centre column's word
+#pragma unroll
+    for (int d = 4; d < 6; d++) {
+        const int dz = (d == 4) ? 1 : -1;
+        const int nfree = (int)((nf6 >> (8 * d)) & 0xff);
+        const bool blocked = (blk6 >> d) & 1u;
+        for (int sN = 1 + lane; sN <= L; sN += G) {
+            float v = -1.0f;
+            if (sN <= nfree) v = k2_value(k2_code(centre_seen, z + dz * sN));
+            else if (sN == nfree + 1 && blocked) v = 2.0f;
+            if (obs_row) obs_row[d * L + sN - 1] = v;
         }
     }
     if (obs_row) {
