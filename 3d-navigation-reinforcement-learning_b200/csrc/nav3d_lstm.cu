@@ -131,6 +131,12 @@ int get_handle(void *stream, cublasHandle_t *out) {
         if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return nav3d::fail_with(NAV3D_ERR_CUDA, "nav3d_lstm: cublasCreate failed");
         if (cublasSetStream(h, (cudaStream_t)stream) != CUBLAS_STATUS_SUCCESS)
             return nav3d::fail_with(NAV3D_ERR_CUDA, "nav3d_lstm: cublasSetStream failed");
+        // An explicit workspace: inside a CUDA-graph capture cuBLAS may not allocate, and a captured GEMM must find the
+        // same workspace at every replay.  (Held for the life of the process, like the handle.)
+        void *ws = nullptr;
+        constexpr size_t kWorkspace = 32u << 20;
+        if (cudaMalloc(&ws, kWorkspace) != cudaSuccess || cublasSetWorkspace(h, ws, kWorkspace) != CUBLAS_STATUS_SUCCESS)
+            return nav3d::fail_with(NAV3D_ERR_CUDA, "nav3d_lstm: cuBLAS workspace allocation failed");
         it = g_handles.emplace(key, h).first;
     }
     *out = it->second;
@@ -162,6 +168,11 @@ cudaError_t pdl_launch(void (*kernel)(KArgs...), unsigned grid, cudaStream_t s, 
 }  // namespace
 
 extern "C" {
+
+int nav3d_lstm_prepare(void *stream) {
+    cublasHandle_t hnd;
+    return get_handle(stream, &hnd);
+}
 
 int nav3d_lstm_forward(const float *x, const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh,
                        const float *h0, const float *c0, const uint8_t *starts, int32_t S, int32_t B, int32_t F, int32_t H,

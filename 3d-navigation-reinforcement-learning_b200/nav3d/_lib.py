@@ -74,6 +74,7 @@ SYMBOLS = {
     "nav3d_restore": (C.c_int, [_P, _P, C.c_size_t]),
     "nav3d_sample_actions": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_int32, _P, _P, _P, _P]),
     "nav3d_gae": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
+    "nav3d_lstm_prepare": (C.c_int, [_P]),
     "nav3d_lstm_forward": (C.c_int, [_P] * 8 + [C.c_int32] * 5 + [_P] * 5),
     "nav3d_lstm_backward": (C.c_int, [_P] * 8 + [C.c_int32] * 5 + [_P] * 5),
     "nav3d_launch_count": (C.c_uint64, [_P]),

@@ -102,11 +102,11 @@ class RecurrentActorCritic(nn.Module):
         """x [S,B,F], starts [S,B] (1 = the state entering step t is zeroed), cuts = sorted timesteps at which a mask
         has to be applied (0 is always one).
 
-        Sequences on a CUDA device go through the library's fused LSTM (``nav3d_lstm_forward/backward``: the episode-start
-        mask is an operand, so nothing is cut, and the backward avoids cuDNN's bulk gate-gradient pass — DESIGN.md §6b).
-        Single steps and CPU tensors use torch's LSTM, run over every stretch between cuts."""
-        if (self.fused_lstm and x.is_cuda and x.shape[0] > 1 and lstm.num_layers == 1 and x.dtype == torch.float32
-                and not torch.cuda.is_current_stream_capturing()):
+        CUDA tensors go through the library's fused LSTM (``nav3d_lstm_forward/backward``: the episode-start mask is an
+        operand, so nothing is cut, and the backward avoids cuDNN's bulk gate-gradient pass — DESIGN.md §6b), single rollout
+        steps included; it is capturable in a CUDA graph once ``train_ops.lstm_prepare_stream`` has run for the capture
+        stream.  CPU tensors and multi-layer LSTMs use torch's LSTM, run over every stretch between cuts."""
+        if self.fused_lstm and x.is_cuda and lstm.num_layers == 1 and x.dtype == torch.float32:
             from .train_ops import fused_lstm
             y, h, c = fused_lstm(x, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, state[0][0],
                                  state[1][0], starts)

@@ -235,10 +235,15 @@ class RecurrentPPO:
         n_chunks = (T + C - 1) // C
         self._g_ep = torch.zeros(3, dtype=torch.float32, device=self.device)
         graphs, pool = [], None
+        if getattr(self, "_roll_stream", None) is None:
+            self._roll_stream = torch.cuda.Stream(device=self.device)
+        if self.policy.fused_lstm:
+            from .train_ops import lstm_prepare_stream
+            lstm_prepare_stream(self._roll_stream)       # the fused LSTM's cuBLAS handle must exist before the capture
         torch.cuda.synchronize(self.device)
         for k in range(n_chunks):
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, pool=pool):
+            with torch.cuda.graph(graph, pool=pool, stream=self._roll_stream):
                 if k == 0:
                     self._g_ep.zero_()
                     self._obs[0].copy_(self._obs[T])
@@ -325,11 +330,14 @@ class RecurrentPPO:
                 self._upd_idx = torch.zeros(b_seq, dtype=torch.int64, device=self.device)
                 self._upd_acc = torch.zeros(6, dtype=torch.float32, device=self.device)
                 self._upd_stream = torch.cuda.Stream(device=self.device)
+                if pol.fused_lstm:
+                    from .train_ops import lstm_prepare_stream
+                    lstm_prepare_stream(self._upd_stream)
             for k, v in fresh.items():
                 self._upd[k].copy_(v)
-            # cuts=None = mask the LSTM state at EVERY timestep: while a graph is being captured the policy runs torch's
-            # LSTM between cuts (policy._run_lstm excludes the fused kernel then), and the replayed minibatches differ in
-            # where their episodes start, so no fixed cut list would be right for all of them.
+            # cuts=None = mask the LSTM state at EVERY timestep.  The fused LSTM (the default: capturable, the episode-start
+            # mask is an operand) ignores cuts; if torch's LSTM runs instead (fused_lstm off, several layers) no fixed cut
+            # list would be right for all the minibatches one captured graph replays.
             data, acc, cuts = self._upd, self._upd_acc, None
             acc.zero_()
             # everything of a captured minibatch lives on ONE stream (also the warm-up runs, so that autograd's gradient

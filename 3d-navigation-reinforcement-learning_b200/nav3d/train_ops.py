@@ -78,6 +78,13 @@ class DeviceOps:
                                       _ptr(returns), _stream(dev)))
 
 
+def lstm_prepare_stream(stream: "torch.cuda.Stream") -> None:
+    """Create the fused LSTM's cuBLAS handle + workspace for `stream` (include/nav3d.h nav3d_lstm_prepare): to be called
+    before a CUDA-graph capture on that stream, after which fused_lstm is capturable on it."""
+    with torch.cuda.device(stream.device):
+        check(_lib.load().nav3d_lstm_prepare(C.c_void_p(stream.cuda_stream)))
+
+
 class _FusedLSTMFn(torch.autograd.Function):
     """``nav3d_lstm_forward`` / ``nav3d_lstm_backward`` as one autograd node: (x, w_ih, w_hh, b_ih, b_hh, h0, c0, starts)
     -> (h_all, h_last, c_last).  Gradients flow to the four parameters only (see include/nav3d.h)."""

@@ -70,7 +70,9 @@ typedef struct {
     int32_t env_kind;             /* nav3d_env_kind */
     int32_t local_map_length;     /* ray length L (CubicEnv.py:25; 10 in train/Grid_Train.py:36) */
     int32_t auto_reset;           /* 1: finished envs reset inside nav3d_step (SB3 VecEnv contract), 0: plain gym */
-    int32_t lanes_per_env;        /* threads cooperating on one env: 1,2,4,8,16,32; 0 = engine default */
+    int32_t lanes_per_env;        /* threads per env: 1 (one thread owns an env; rows leave through a shared-memory
+                                     staging tile, written by the warp), 2,4,8,16,32 (lanes cooperate on one env);
+                                     0 = engine default = 1 (simpleEnv with 6L+7 > 95: 2) */
     uint32_t env_id0;             /* global id of local env 0 (sharding) */
     uint64_t seed;                /* Philox key */
     double crash_penalty;         /* CubicEnv.py:28, -2.0 */
@@ -177,8 +179,9 @@ int nav3d_step_host(nav3d_engine *e, const int64_t *actions, float *obs, float *
                     uint8_t *truncated);
 
 /* T fused steps with uniform random actions from the env's Philox action stream (indices t0 .. t0+T-1):
- * the "synthetic random-action rollout" of BASELINE.json.  One launch; each env's steps run back to back.
- *   obs    : DEVICE f32[T][n_envs][obs_dim] or NULL (then only the last observation is kept in obs_last)
+ * the "synthetic random-action rollout" of BASELINE.json.  One launch; each env's steps run back to back with its record
+ * in registers, and every step does the full work of nav3d_step (marking, window gather, reward, auto-reset).
+ *   obs    : DEVICE f32[T][n_envs][obs_dim] or NULL (then only the last observation is written, to obs_last)
  *   obs_last: DEVICE f32[n_envs][obs_dim] or NULL
  *   reward : DEVICE f32[T][n_envs] or NULL;  done : DEVICE u8[T][n_envs] or NULL (terminated | truncated)
  *   actions_out : DEVICE u8[T][n_envs] or NULL */
@@ -231,6 +234,10 @@ int nav3d_gae(const float *rewards, const float *values, const uint8_t *episode_
  *   x f32[S][B][F]; h0, c0 f32[B][H]; starts u8[S][B] (1 = the state entering step t is zeroed)
  *   out: gates f32[S][B][4H] (activated i,f,g,o, kept for backward), h_in f32[S][B][H] (masked state entering each step),
  *        h_all, c_all f32[S][B][H] (h_all is the layer output; the final state is row S-1 of h_all / c_all) */
+/* Creates the cuBLAS handle + workspace the two calls below use on `stream` (they do it lazily otherwise).  Call it BEFORE a
+ * CUDA-graph capture on that stream begins: handle creation allocates, which a capture forbids; afterwards
+ * nav3d_lstm_forward / nav3d_lstm_backward are capturable on it. */
+int nav3d_lstm_prepare(void *stream);
 int nav3d_lstm_forward(const float *x, const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh,
                        const float *h0, const float *c0, const uint8_t *starts, int32_t S, int32_t B, int32_t F, int32_t H,
                        int32_t tf32, float *gates, float *h_in, float *h_all, float *c_all, void *stream);
