@@ -190,14 +190,20 @@ NAV3D_HD void store_stream(float *p, float v) {
 #endif
 }
 
-// Observation rows.  Direct: a lane streams its float4 straight to the caller's row.  STAGED (thread-per-env kernels): the
-// row is first assembled in the thread's slot of a shared-memory staging tile (kStageStride floats apart: 84 mod 32 = 20
-// spreads the 32 rows' float4 over all banks) and the WARP then writes the 32 rows out with fully coalesced 128-bit stores
-// (flush_rows in nav3d_engine.cu) — 16 full sectors per store instruction instead of 32 half sectors.
-constexpr int kStageStride = 84;
-template <bool STAGED> NAV3D_HD void row_store(float *row, int j, float4 v) {
-    if (STAGED) reinterpret_cast<float4 *>(row)[j] = v;
-    else store_stream(reinterpret_cast<float4 *>(row) + j, v);
+// Observation rows.  Direct: a lane streams its float4 straight to the caller's row.  STAGED (thread-per-env kernels): a
+// thread leaves its row in COMPACT form in its slot of a shared-memory staging tile — kStageStride u32 apart (odd: the 32
+// rows fall into 32 different banks): words 0..15 the sixteen window columns as four 5-bit codes each, word 16 the packed
+// scalars, word 17 the f32 bits of visited / total — and the WARP then expands the 32 rows through the code table and writes
+// them out with fully coalesced 128-bit stores (flush_rows in nav3d_engine.cu): 16 full sectors per store instruction
+// instead of 32 half sectors, and 100 bytes of shared memory per env instead of 336.
+constexpr int kStageStride = 25;
+constexpr int kStageScalars = 16, kStageExplored = 17;
+NAV3D_HD uint32_t float_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; __builtin_memcpy(&u, &f, 4); return u;
+#endif
 }
 
 template <int G> NAV3D_HD unsigned group_mask(int lane_in_warp) {
@@ -369,7 +375,12 @@ NAV3D_HD uint32_t window_quad(uint32_t lo, uint32_t hi, int s) {
 template <int G, bool STAGED = false>
 NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &sc, const float *lut,
                             float *__restrict__ obs_row) {
-    for (int j = 16 + lane; j < 20; j += G) {
+    if (STAGED) {          // compact: facing | last_action << 2 | was_near_wall << 5 | last_bump << 6 | down << 8
+        uint32_t *row = reinterpret_cast<uint32_t *>(obs_row);
+        row[kStageScalars] = (uint32_t)sc.facing | ((uint32_t)sc.last_action << 2) | ((uint32_t)sc.was_near_wall << 5) |
+                             ((uint32_t)sc.last_bump << 6) | ((uint32_t)sc.down << 8);
+        row[kStageExplored] = float_bits(fdiv_rn((float)sc.visited, (float)sc.total_free));
+    } else for (int j = 16 + lane; j < 20; j += G) {
         float4 v;
         if (j == 16) {
             v.x = sc.facing == 0 ? 1.f : 0.f; v.y = sc.facing == 1 ? 1.f : 0.f;
@@ -388,7 +399,7 @@ NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &s
         } else {
             v.x = v.y = v.z = v.w = 0.f;
         }
-        row_store<STAGED>(obs_row, j, v);
+        store_stream(reinterpret_cast<float4 *>(obs_row) + j, v);
     }
 }
 
@@ -608,10 +619,13 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
                     if (dxi == 2 && dyi == 1) nbr |= mid << 15;    // -y
                 }
                 if (obs_row != nullptr) {
-                    float4 v;
-                    v.x = lut[quad & 31u]; v.y = lut[(quad >> 5) & 31u];
-                    v.z = lut[(quad >> 10) & 31u]; v.w = lut[quad >> 15];
-                    row_store<STAGED>(obs_row, dxi * 4 + dyi, v);
+                    if (STAGED) reinterpret_cast<uint32_t *>(obs_row)[dxi * 4 + dyi] = quad;
+                    else {
+                        float4 v;
+                        v.x = lut[quad & 31u]; v.y = lut[(quad >> 5) & 31u];
+                        v.z = lut[(quad >> 10) & 31u]; v.w = lut[quad >> 15];
+                        store_stream(reinterpret_cast<float4 *>(obs_row) + (dxi * 4 + dyi), v);
+                    }
                 }
             }
         }

@@ -180,19 +180,44 @@ __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_co
 // by the one thread that needs it, and the only cooperation is in data movement — the warp writes the 32 observation rows
 // it assembled in shared memory with coalesced 128-bit stores, and clears the knowledge of the envs it resets together.
 // ---------------------------------------------------------------------------------------------------------------
-// The warp's 32 staged rows -> their global rows (dst[e] == NULL: env e has none).  8 envs x 20 float4 = 5 x 32 float4.
-__device__ __forceinline__ void flush_rows(const float *stage, float *const *dst, int lane) {
+// The warp's 32 staged (compact) rows -> their global rows (dst[e] == NULL: env e has none): get_obs Steps 2-6
+// (CubicEnv.py:270-307) — clip to [-2, 20] and (m + 2) / 22 through the code table, facing one-hot, the scalar quotients,
+// zero padding.  Two passes so that every store instruction runs ONE code path: the 16 window float4 of two envs per
+// instruction (lane l: column l % 16 of env 2i + l / 16: 2 x 256 contiguous bytes), then the 4 scalar float4 of eight envs
+// per instruction (lane l: quad 16 + l % 4 of env 8i + l / 4: 8 x 64 contiguous bytes).
+__device__ __forceinline__ void flush_rows(const float *stage_f, float *const *dst, int lane, const float *lut, int L) {
+    const uint32_t *stage = reinterpret_cast<const uint32_t *>(stage_f);
     __syncwarp();
+    const int j = lane & 15, eh = lane >> 4;
+#pragma unroll 4
+    for (int i = 0; i < 16; i++) {
+        const int e = 2 * i + eh;
+        float *d = dst[e];
+        if (d == nullptr) continue;                                // (a row that was not staged holds stale words)
+        const uint32_t q = stage[e * kStageStride + j];
+        float4 v;
+        v.x = lut[q & 31u]; v.y = lut[(q >> 5) & 31u]; v.z = lut[(q >> 10) & 31u]; v.w = lut[q >> 15];
+        __stcs(reinterpret_cast<float4 *>(d) + j, v);
+    }
+    const int k = lane & 3, e4 = lane >> 2;
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const int idx = i * 32 + lane, e8 = idx / 20, j = idx - e8 * 20;
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const int e = g * 8 + e8;
-            float *d = dst[e];
-            if (d != nullptr)
-                __stcs(reinterpret_cast<float4 *>(d) + j, reinterpret_cast<const float4 *>(stage + e * kStageStride)[j]);
-        }
+    for (int i = 0; i < 4; i++) {
+        const int e = 8 * i + e4;
+        float *d = dst[e];
+        if (d == nullptr) continue;
+        const uint32_t sc = stage[e * kStageStride + kStageScalars], down = sc >> 8;
+        const float ex = __uint_as_float(stage[e * kStageStride + kStageExplored]);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k == 0) {                                              // facing one-hot (:279-280)
+            const uint32_t f = sc & 3u;
+            v.x = f == 0 ? 1.f : 0.f; v.y = f == 1 ? 1.f : 0.f; v.z = f == 2 ? 1.f : 0.f; v.w = f == 3 ? 1.f : 0.f;
+        } else if (k == 1) {                                       // last_action / 5, was_near_wall, last_bump, down / L (:284-287)
+            v.x = lut[kLutFifth + ((sc >> 2) & 7u)];
+            v.y = (float)((sc >> 5) & 1u);
+            v.z = (float)((sc >> 6) & 1u);
+            v.w = L <= 31 ? lut[kLutDown + down] : __fdiv_rn((float)down, (float)L);
+        } else if (k == 2) v.x = ex;                               // visited / total (:291); quad 19 is padding
+        __stcs(reinterpret_cast<float4 *>(d) + 16 + k, v);
     }
     __syncwarp();
 }
@@ -223,13 +248,13 @@ __device__ __noinline__ void tpe_reset(const EngineParams &P, bool mine, uint32_
         const uint32_t nbr = reset_lane<1, STAGED>(P, (int)env, 0, room, k, episode + 1u, lut, row, c);
         reset_commit(P, (int)env, 0, c, nbr);
     }
-    if (STAGED) flush_rows(stage, dst, lane);
+    if (STAGED) flush_rows(stage, dst, lane, lut, P.L);
 }
 
 template <int BLOCK, bool STAGED>
 __device__ __forceinline__ void step_tpe_body(const EngineParams &P, const StepIO &io) {
     __shared__ float lut[kLutSize];
-    __shared__ __align__(16) float stage_all[STAGED ? BLOCK * kStageStride : 4];
+    __shared__ float stage_all[STAGED ? BLOCK * kStageStride : 4];
     __shared__ float *dst_all[STAGED ? BLOCK : 1];
     asm volatile("griddepcontrol.launch_dependents;");          // programmatic dependent launch, as in step_call_kernel
     fill_lut(lut, P.L);
@@ -246,7 +271,7 @@ __device__ __forceinline__ void step_tpe_body(const EngineParams &P, const StepI
     if (valid)
         rst = step_env<1, false, STAGED>(P, io, (int)env, 0, lane, (int)io.actions[env], lut, env, nullptr, nullptr,
                                          stage + lane * kStageStride, dst + lane);
-    if (STAGED) flush_rows(stage, dst, lane);
+    if (STAGED) flush_rows(stage, dst, lane, lut, P.L);
     if (__any_sync(0xffffffffu, rst)) {
         const uint32_t episode = rst ? P.states[env].episode : 0u;   // untouched by a step that ends its episode
         tpe_reset<STAGED>(P, rst, (uint32_t)env, episode, false, 0u, 0u, lut, io.obs, stage, dst, lane);
@@ -266,7 +291,7 @@ __global__ void __launch_bounds__(kBlock) reset_tpe_kernel(const __grid_constant
                                                            const int32_t *__restrict__ env_ids, int n,
                                                            const int32_t *__restrict__ picks, float *obs) {
     __shared__ float lut[kLutSize];
-    __shared__ __align__(16) float stage_all[kBlock * kStageStride];
+    __shared__ float stage_all[kBlock * kStageStride];
     __shared__ float *dst_all[kBlock];
     fill_lut(lut, P.L);
     const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
@@ -296,7 +321,7 @@ template <int BLOCK, bool STAGED>
 __device__ __forceinline__ void rollout_tpe_body(const EngineParams &P, int T, uint32_t t0, float *obs, float *obs_last,
                                                  float *reward, uint8_t *done, uint8_t *actions_out) {
     __shared__ float lut[kLutSize];
-    __shared__ __align__(16) float stage_all[STAGED ? BLOCK * kStageStride : 4];
+    __shared__ float stage_all[STAGED ? BLOCK * kStageStride : 4];
     __shared__ float *dst_all[STAGED ? BLOCK : 1];
     fill_lut(lut, P.L);
     const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
@@ -329,7 +354,7 @@ __device__ __forceinline__ void rollout_tpe_body(const EngineParams &P, int T, u
             if (done) done[(long long)t * N + env] = bits ? 1 : 0;
             if (actions_out) actions_out[(long long)t * N + env] = (uint8_t)action;
         }
-        if (STAGED) flush_rows(stage, dst, lane);
+        if (STAGED) flush_rows(stage, dst, lane, lut, P.L);
         if (__any_sync(0xffffffffu, rst)) {
             tpe_reset<STAGED>(P, rst, (uint32_t)env, st.episode, false, 0u, 0u, lut, io.obs, stage, dst, lane);
             if (rst) st = P.states[env];           // the new episode's record (written by this very thread)
@@ -1030,6 +1055,9 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
             if (tblock == 64)
                 rollout_tpe144_kernel<<<(unsigned)((e->cfg.n_envs + 63) / 64), 64, 0, s>>>(e->P, T, t0, obs, obs_last,
                                                                                                   reward, done, actions_out);
+            else if (e->minb == 4)
+                rollout_tpe_kernel<128, 4, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward,
+                                                                                            done, actions_out);
             else
                 rollout_tpe_kernel<128, 3, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward,
                                                                                             done, actions_out);
