@@ -403,6 +403,19 @@ NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &s
     }
 }
 
+// Ray marking by the WARP (thread-per-env kernels).  With one thread per env a warp executes the union of its 32 envs'
+// paths: marking in the thread costs every lane the longest run of the warp.  Instead a thread on a first visit only
+// QUEUES its marking tiles — one u32 per tile: word index of the tile in the env's block (16 bits) | lane (5) << 16 | cell
+// mask (4) << 21 | z field (3) << 25 | y-run (words tile + j instead of tile + 4j) << 28 | wall code instead of seen << 29 —
+// in a shared-memory list of the warp, and after the step all 32 lanes work the list off evenly (coop_marks in
+// nav3d_engine.cu).  No two tasks of a step touch the same word, so their order does not matter.
+struct MarkQueue {
+    uint32_t *tasks;               // the warp's list (kMarkQueueCap entries)
+    int *count;                    // its length
+    int lane;                      // this thread's lane (the flush finds the env's block through it)
+};
+constexpr int kMarkQueueCap = 32 * 40;      // per lane at most 2 x 17 tiles (rooms are at most 64 cells wide + border) + 4 wall ends
+
 // A code-0 field at bit `sh` of w becomes `code`; returns the new word.
 NAV3D_HD uint32_t mark_field(uint32_t w, int sh, uint32_t code) { return ((w >> sh) & 31u) ? w : (w | (code << sh)); }
 
@@ -449,7 +462,7 @@ NAV3D_HD void centre_update(uint32_t *cw, int nzb, int z, int c_new, bool mark, 
 template <int G, bool STAGED = false>
 NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk, int lane, int x, int y, int z,
                           const Rays &r, int c_new, bool fresh, bool persist, int mdir, const ObsScalars &sc,
-                          const float *lut, float *__restrict__ obs_row) {
+                          const float *lut, float *__restrict__ obs_row, const MarkQueue *mq = nullptr) {
     using M = WinMap<G>;
     uint32_t *__restrict__ K = reinterpret_cast<uint32_t *>(envk);
     const int L = P.L, nzb = R.nzb;
@@ -549,12 +562,31 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
                 if (((ym[u] >> j) & 1u) && ((yv[j] >> zsh) & 31u) == 0u) K[by + j] = yv[j] | (kCodeSeen << zsh);
         }
     };
-    tiles_load(xt0, yt0);
     const bool pon[4] = {wxh, wxl, wyh, wyl};
     const uint32_t pidx[4] = {k_xpart(R, r.x1 + kPadLo) + xbase, k_xpart(R, r.x0 + kPadLo) + xbase,
                               k_ypart(R, r.y1 + kPadLo) + ybase, k_ypart(R, r.y0 + kPadLo) + ybase};
+    const bool queued = STAGED && mq != nullptr;               // the warp marks (coop_marks): only queue the tiles here
+#ifdef __CUDA_ARCH__
+    if (queued && mark) {
+        const int nx = xt1 - xt0 + 1, ny = yt1 - yt0 + 1;        // >= 0 each
+        const int np = (int)wxh + (int)wxl + (int)wyh + (int)wyl;
+        const int n = nx + ny + np;
+        if (n > 0) {
+            int at = atomicAdd(mq->count, n);
+            const uint32_t tag = ((uint32_t)mq->lane << 16) | ((uint32_t)(z - 6 * zbz) << 25);
+            for (int T = xt0; T <= xt1; T++)
+                mq->tasks[at++] = (xbase + (uint32_t)T * xmul) | tag | (tile_mask(xrm, T) << 21);
+            for (int T = yt0; T <= yt1; T++)
+                mq->tasks[at++] = (ybase + (uint32_t)T * ymul) | tag | (tile_mask(yrm, T) << 21) | (1u << 28);
 #pragma unroll
-    for (int d = 0; d < 4; d++) pw[d] = (pon[d] && (d & (G - 1)) == lane) ? K[pidx[d]] : 0xffffffffu;
+            for (int d = 0; d < 4; d++)
+                if (pon[d]) mq->tasks[at++] = pidx[d] | tag | (1u << 21) | (1u << 29);
+        }
+    }
+#endif
+    if (!queued) tiles_load(xt0, yt0);
+#pragma unroll
+    for (int d = 0; d < 4; d++) pw[d] = (!queued && pon[d] && (d & (G - 1)) == lane) ? K[pidx[d]] : 0xffffffffu;
     // The owner of the centre column loads all of its words: counter update + the z rays.
     bool owner = false;
 #pragma unroll
@@ -575,14 +607,16 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
 #pragma unroll
         for (int b = 0; b < 3; b++) if (b < nzb && persist && cw[b] != cw_old[b]) K[cbase + ((uint32_t)b << 4)] = cw[b];
     }
-    tiles_store(xt0, yt0);
+    if (!queued) {
+        tiles_store(xt0, yt0);
 #pragma unroll
-    for (int d = 0; d < 4; d++)
-        if (((pw[d] >> zsh) & 31u) == 0u) K[pidx[d]] = pw[d] | (kCodeWall << zsh);
-    // the rest of long runs, both runs per round so that their loads share one latency
-    for (int k = G * UT; xt0 + k <= xt1 || yt0 + k <= yt1; k += G * UT) {
-        tiles_load(xt0 + k, yt0 + k);
-        tiles_store(xt0 + k, yt0 + k);
+        for (int d = 0; d < 4; d++)
+            if (((pw[d] >> zsh) & 31u) == 0u) K[pidx[d]] = pw[d] | (kCodeWall << zsh);
+        // the rest of long runs, both runs per round so that their loads share one latency
+        for (int k = G * UT; xt0 + k <= xt1 || yt0 + k <= yt1; k += G * UT) {
+            tiles_load(xt0 + k, yt0 + k);
+            tiles_store(xt0 + k, yt0 + k);
+        }
     }
 
     // ---- 3. the window: clip to [-2, 20], (m + 2) / 22 (:273-275), one float4 per column; neighbour codes
@@ -651,7 +685,8 @@ NAV3D_HD void reset_clear(const EngineParams &P, int env, int lane, uint32_t roo
 
 template <int G, bool STAGED = false>
 NAV3D_HD uint32_t reset_lane(const EngineParams &P, int env, int lane, uint32_t room_idx, uint32_t k,
-                             uint32_t episode_after, const float *lut, float *obs_row, ResetCtx &c) {
+                             uint32_t episode_after, const float *lut, float *obs_row, ResetCtx &c,
+                             const MarkQueue *mq = nullptr) {
     const RoomDev R = P.rooms[room_idx];
     uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
     uint32_t cell = ldg(P.free_cells + R.free_off + k);               // possible_start_pose[k] (:450-462)
@@ -666,7 +701,7 @@ NAV3D_HD uint32_t reset_lane(const EngineParams &P, int env, int lane, uint32_t 
     sc.facing = 0; sc.last_action = 0; sc.was_near_wall = 0; sc.last_bump = 0; sc.down = c.r.down;
     sc.visited = 1; sc.total_free = R.n_free;
     // internal_grid[start] = 1 (:85), then the first sensing pass
-    return observe<G, STAGED>(P, R, envk, lane, c.x, c.y, c.z, c.r, 1, true, true, -1, sc, lut, obs_row);
+    return observe<G, STAGED>(P, R, envk, lane, c.x, c.y, c.z, c.r, 1, true, true, -1, sc, lut, obs_row, mq);
 }
 
 NAV3D_HD void reset_commit(const EngineParams &P, int env, int lane, const ResetCtx &c, uint32_t nbr) {
@@ -725,7 +760,7 @@ struct StepCtx {                   // what the second half needs; identical in e
 template <int G, bool REG_STATE = false, bool STAGED = false>
 NAV3D_HD uint32_t step_lane(const EngineParams &P, const StepIO &io, int env, int lane, int action, const float *lut,
                             long long row /* row index for the output arrays */, const EnvState *rs, StepCtx &c,
-                            float *stage_row = nullptr, float **dst_slot = nullptr) {
+                            float *stage_row = nullptr, float **dst_slot = nullptr, const MarkQueue *mq = nullptr) {
     const EnvState st = REG_STATE ? *rs : P.states[env];
     const RoomDev R = P.rooms[st.room];
     uint8_t *envk = P.know + (unsigned long long)env * P.env_stride;
@@ -783,7 +818,7 @@ NAV3D_HD uint32_t step_lane(const EngineParams &P, const StepIO &io, int env, in
     if (STAGED) { *dst_slot = orow; if (orow != nullptr) orow = stage_row; }
     if (c.will_reset && orow == nullptr) return 0u;        // nothing observes the last state of the episode
     return observe<G, STAGED>(P, R, envk, lane, x, y, z, r, c.c_new, c.explored, !c.will_reset, moved ? (int)dir : -2, sc,
-                              lut, orow);
+                              lut, orow, mq);
 }
 
 template <int G, bool REG_STATE = false>
@@ -846,9 +881,9 @@ NAV3D_HD void step_commit(const EngineParams &P, const StepIO &io, int env, int 
 template <int G, bool REG_STATE = false, bool STAGED = false>
 NAV3D_HD bool step_env(const EngineParams &P, const StepIO &io, int env, int lane, int lane_in_warp, int action,
                        const float *lut, long long row, EnvState *rs = nullptr, uint32_t *done_bits = nullptr,
-                       float *stage_row = nullptr, float **dst_slot = nullptr) {
+                       float *stage_row = nullptr, float **dst_slot = nullptr, const MarkQueue *mq = nullptr) {
     StepCtx c;
-    const uint32_t part = step_lane<G, REG_STATE, STAGED>(P, io, env, lane, action, lut, row, rs, c, stage_row, dst_slot);
+    const uint32_t part = step_lane<G, REG_STATE, STAGED>(P, io, env, lane, action, lut, row, rs, c, stage_row, dst_slot, mq);
     step_commit<G, REG_STATE>(P, io, env, lane, c, group_or<G>(part, lane_in_warp), row, rs, done_bits);
     return c.will_reset;
 }

@@ -222,12 +222,60 @@ __device__ __forceinline__ void flush_rows(const float *stage_f, float *const *d
     __syncwarp();
 }
 
+// Per-warp shared-memory workspace of the thread-per-env kernels: the staged rows with their destinations, and the warp's
+// list of marking tiles with the env each lane plays.
+struct WarpWork {
+    float stage[32 * kStageStride];
+    float *dst[32];
+    uint32_t tasks[kMarkQueueCap];
+    uint32_t env_of_lane[32];
+    int n_tasks;
+};
+
+// Step 1 of get_obs (CubicEnv.py:264-266) for the x / y rays of every env of the warp that is on a first visit: the lanes
+// share the queued tiles evenly.  A task is up to four words of one tile (x run: words tile + 4j, y run: tile + j, a wall
+// end: one word); a word whose field at the agent's height is still 0 (unknown) becomes "seen" (2) or "known wall" (1).
+// `between` (the row flush) runs while the first round's loads are in flight.
+template <typename F>
+__device__ __forceinline__ void coop_marks(const EngineParams &P, WarpWork *w, int lane, F &&between) {
+    __syncwarp();                                                // every lane has queued its tiles
+    const int total = w->n_tasks;
+    constexpr int CH = 4;                                        // tasks per lane per round: all loads before the first use
+    bool first = true;
+    for (int i0 = 0; i0 < total || first; i0 += 32 * CH) {
+        uint32_t v[CH][4], meta[CH];
+        uint32_t *Kp[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int i = i0 + c * 32 + lane;
+            const uint32_t t = i < total ? w->tasks[i] : 0u;     // 0: empty mask
+            meta[c] = t;
+            Kp[c] = reinterpret_cast<uint32_t *>(P.know + (unsigned long long)w->env_of_lane[(t >> 16) & 31u] * P.env_stride) +
+                    (t & 0xffffu);
+            const uint32_t m = (t >> 21) & 15u, stride = (t & (1u << 28)) ? 1u : 4u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[c][j] = ((m >> j) & 1u) ? Kp[c][j * stride] : 0xffffffffu;
+        }
+        if (first) { between(); first = false; }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const uint32_t t = meta[c], zsh = 5u * ((t >> 25) & 7u), stride = (t & (1u << 28)) ? 1u : 4u;
+            const uint32_t code = ((t & (1u << 29)) ? kCodeWall : kCodeSeen) << zsh;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (((v[c][j] >> zsh) & 31u) == 0u) Kp[c][j * stride] = v[c][j] | code;
+        }
+    }
+    __syncwarp();                                                // the marks are visible to the warp's next loads
+    if (lane == 0) w->n_tasks = 0;
+    __syncwarp();
+}
+
 // Auto-reset of the warp's envs whose lanes say `mine` (CubicEnv.py:77-108 with Philox picks).  Out of line so that the
 // step keeps its registers.  The new record goes to P.states.
 template <bool STAGED>
 __device__ __noinline__ void tpe_reset(const EngineParams &P, bool mine, uint32_t env, uint32_t episode, bool have_picks,
-                                       uint32_t room, uint32_t k, const float *lut, float *obs, float *stage,
-                                       float **dst, int lane) {
+                                       uint32_t room, uint32_t k, const float *lut, float *obs, WarpWork *w, int lane) {
     const unsigned rmask = __ballot_sync(0xffffffffu, mine);
     if (mine && !have_picks) reset_picks(P, (int)env, episode, room, k);
     // internal_grid = full(-1) (:84): the whole warp sweeps each env's bricks
@@ -240,61 +288,60 @@ __device__ __noinline__ void tpe_reset(const EngineParams &P, bool mine, uint32_
         for (uint32_t i = (uint32_t)lane; i < n; i += 32u) k4[i] = zero;
     }
     __syncwarp();
-    if (STAGED) dst[lane] = nullptr;
+    if (STAGED) w->dst[lane] = nullptr;
     if (mine) {
         ResetCtx c;
         float *row = obs ? obs + (unsigned long long)env * kObsDim : nullptr;
-        if (STAGED) { dst[lane] = row; if (row) row = stage + lane * kStageStride; }
-        const uint32_t nbr = reset_lane<1, STAGED>(P, (int)env, 0, room, k, episode + 1u, lut, row, c);
+        MarkQueue mq{w->tasks, &w->n_tasks, lane};
+        if (STAGED) { w->dst[lane] = row; if (row) row = w->stage + lane * kStageStride; }
+        const uint32_t nbr = reset_lane<1, STAGED>(P, (int)env, 0, room, k, episode + 1u, lut, row, c, STAGED ? &mq : nullptr);
         reset_commit(P, (int)env, 0, c, nbr);
     }
-    if (STAGED) flush_rows(stage, dst, lane, lut, P.L);
+    if (STAGED) coop_marks(P, w, lane, [&]() { flush_rows(w->stage, w->dst, lane, lut, P.L); });
 }
 
 template <int BLOCK, bool STAGED>
 __device__ __forceinline__ void step_tpe_body(const EngineParams &P, const StepIO &io) {
     __shared__ float lut[kLutSize];
-    __shared__ float stage_all[STAGED ? BLOCK * kStageStride : 4];
-    __shared__ float *dst_all[STAGED ? BLOCK : 1];
+    __shared__ WarpWork work[STAGED ? BLOCK / 32 : 1];
     asm volatile("griddepcontrol.launch_dependents;");          // programmatic dependent launch, as in step_call_kernel
     fill_lut(lut, P.L);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-    float *stage = stage_all + wbase * kStageStride;
-    float **dst = dst_all + wbase;
+    const int lane = threadIdx.x & 31;
+    WarpWork *w = work + (STAGED ? threadIdx.x >> 5 : 0);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (gid - lane >= io.env_n) return;                          // the whole warp is past the range
     const bool valid = gid < io.env_n;
     const long long env = io.env0 + gid;
-    if (STAGED) dst[lane] = nullptr;
+    if (STAGED) {
+        w->dst[lane] = nullptr; w->env_of_lane[lane] = (uint32_t)env;
+        if (lane == 0) w->n_tasks = 0;
+        __syncwarp();
+    }
     bool rst = false;
-    if (valid)
+    if (valid) {
+        MarkQueue mq{w->tasks, &w->n_tasks, lane};
         rst = step_env<1, false, STAGED>(P, io, (int)env, 0, lane, (int)io.actions[env], lut, env, nullptr, nullptr,
-                                         stage + lane * kStageStride, dst + lane);
-    if (STAGED) flush_rows(stage, dst, lane, lut, P.L);
+                                         w->stage + lane * kStageStride, w->dst + lane, STAGED ? &mq : nullptr);
+    }
+    if (STAGED) coop_marks(P, w, lane, [&]() { flush_rows(w->stage, w->dst, lane, lut, P.L); });
     if (__any_sync(0xffffffffu, rst)) {
         const uint32_t episode = rst ? P.states[env].episode : 0u;   // untouched by a step that ends its episode
-        tpe_reset<STAGED>(P, rst, (uint32_t)env, episode, false, 0u, 0u, lut, io.obs, stage, dst, lane);
+        tpe_reset<STAGED>(P, rst, (uint32_t)env, episode, false, 0u, 0u, lut, io.obs, w, lane);
     }
 }
 template <int BLOCK, int MINB, bool STAGED>
 __global__ void __launch_bounds__(BLOCK, MINB) step_tpe_kernel(const __grid_constant__ EngineParams P, StepIO io) {
     step_tpe_body<BLOCK, STAGED>(P, io);
 }
-// 64-thread CTAs capped at 144 registers: 14 warps per SM instead of 12 (7 CTAs), which also divides the 131 072-, 262 144-
-// and 524 288-env shards of the multi-GPU job into whole waves (27.7 / 55.4 / 110.7 warps per SM: 2 / 4 / 8 waves of 14)
-__global__ void __maxnreg__(144) step_tpe144_kernel(const __grid_constant__ EngineParams P, StepIO io) {
-    step_tpe_body<64, true>(P, io);
-}
-
 __global__ void __launch_bounds__(kBlock) reset_tpe_kernel(const __grid_constant__ EngineParams P,
                                                            const int32_t *__restrict__ env_ids, int n,
                                                            const int32_t *__restrict__ picks, float *obs) {
     __shared__ float lut[kLutSize];
-    __shared__ float stage_all[kBlock * kStageStride];
-    __shared__ float *dst_all[kBlock];
+    __shared__ WarpWork work[kBlock / 32];
     fill_lut(lut, P.L);
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const int lane = threadIdx.x & 31;
+    WarpWork *w = work + (threadIdx.x >> 5);
     const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (idx - lane >= n) return;
     int env = idx < n ? (env_ids ? env_ids[idx] : (int)idx) : -1;
@@ -310,8 +357,10 @@ __global__ void __launch_bounds__(kBlock) reset_tpe_kernel(const __grid_constant
             k = k < nf ? k : nf - 1u;
         }
     }
-    tpe_reset<true>(P, mine, (uint32_t)env, episode, picks != nullptr, room, k, lut, obs, stage_all + wbase * kStageStride,
-                    dst_all + wbase, lane);
+    w->env_of_lane[lane] = mine ? (uint32_t)env : 0u;
+    if (lane == 0) w->n_tasks = 0;
+    __syncwarp();
+    tpe_reset<true>(P, mine, (uint32_t)env, episode, picks != nullptr, room, k, lut, obs, w, lane);
 }
 
 // T fused steps per env, thread per env (on-device Philox actions).  The record stays in the
@@ -321,17 +370,21 @@ template <int BLOCK, bool STAGED>
 __device__ __forceinline__ void rollout_tpe_body(const EngineParams &P, int T, uint32_t t0, float *obs, float *obs_last,
                                                  float *reward, uint8_t *done, uint8_t *actions_out) {
     __shared__ float lut[kLutSize];
-    __shared__ float stage_all[STAGED ? BLOCK * kStageStride : 4];
-    __shared__ float *dst_all[STAGED ? BLOCK : 1];
+    __shared__ WarpWork work[STAGED ? BLOCK / 32 : 1];
     fill_lut(lut, P.L);
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-    float *stage = stage_all + wbase * kStageStride;
-    float **dst = dst_all + wbase;
+    const int lane = threadIdx.x & 31;
+    WarpWork *w = work + (STAGED ? threadIdx.x >> 5 : 0);
     const long long gid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     const long long N = P.n_envs;
     if (gid - lane >= N) return;
     const bool valid = gid < N;
     const long long env = gid;
+    if (STAGED) {
+        w->env_of_lane[lane] = (uint32_t)env;
+        if (lane == 0) w->n_tasks = 0;
+        __syncwarp();
+    }
+    const MarkQueue mq{w->tasks, &w->n_tasks, lane};
     EnvState st;
     if (valid) st = P.states[env];
     for (int t = 0; t < T; t++) {
@@ -343,20 +396,20 @@ __device__ __forceinline__ void rollout_tpe_body(const EngineParams &P, int T, u
         io.reward64 = nullptr; io.terminated = nullptr; io.truncated = nullptr;
         io.terminal_obs = nullptr; io.episodes = nullptr;
         io.env0 = 0; io.env_n = P.n_envs;
-        if (STAGED) dst[lane] = nullptr;
+        if (STAGED) w->dst[lane] = nullptr;
         bool rst = false;
         if (valid) {
             uint32_t u0, u1, bits = 0;
             philox4x32_10(P.env_id0 + (uint32_t)env, t0 + (uint32_t)t, 0u, kStreamAction, P.seed_lo, P.seed_hi, u0, u1);
             const int action = (int)mulhi_range(u0, 6u);
             rst = step_env<1, true, STAGED>(P, io, (int)env, 0, lane, action, lut, env, &st, &bits,
-                                            stage + lane * kStageStride, dst + lane);
+                                            w->stage + lane * kStageStride, w->dst + lane, STAGED ? &mq : nullptr);
             if (done) done[(long long)t * N + env] = bits ? 1 : 0;
             if (actions_out) actions_out[(long long)t * N + env] = (uint8_t)action;
         }
-        if (STAGED) flush_rows(stage, dst, lane, lut, P.L);
+        if (STAGED) coop_marks(P, w, lane, [&]() { flush_rows(w->stage, w->dst, lane, lut, P.L); });
         if (__any_sync(0xffffffffu, rst)) {
-            tpe_reset<STAGED>(P, rst, (uint32_t)env, st.episode, false, 0u, 0u, lut, io.obs, stage, dst, lane);
+            tpe_reset<STAGED>(P, rst, (uint32_t)env, st.episode, false, 0u, 0u, lut, io.obs, w, lane);
             if (rst) st = P.states[env];           // the new episode's record (written by this very thread)
         }
     }
@@ -368,11 +421,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) rollout_tpe_kernel(const __grid_c
                                                                   uint8_t *actions_out) {
     rollout_tpe_body<BLOCK, STAGED>(P, T, t0, obs, obs_last, reward, done, actions_out);
 }
-__global__ void __maxnreg__(144) rollout_tpe144_kernel(const __grid_constant__ EngineParams P, int T, uint32_t t0, float *obs,
-                                                       float *obs_last, float *reward, uint8_t *done, uint8_t *actions_out) {
-    rollout_tpe_body<64, true>(P, T, t0, obs, obs_last, reward, done, actions_out);
-}
-
 // T fused steps per env with on-device Philox actions.  An env's record and the knowledge lines it
 // touches stay in L1/L2 for the whole rollout, so DRAM sees the outputs the caller asked for plus one pass over the touched
 // lines.  When only the last observation is requested the intermediate observations are never formed.  The reset is an
@@ -949,13 +997,12 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
         }
         if (G == 1) {                                  // thread per env: staged, coalesced observation stores
             static const bool staged = !(getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) == 0);
-            // 64-thread CTAs at 144 registers for shards below two full waves of the 128-thread kernel (measured: 65 536
-            // envs 24.6 -> 20.9 us per step; no gain from 131 072 envs on), NAV3D_TPE_BLOCK overrides
-            static const int tblock_env = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 0;
-            const int tblock = tblock_env ? tblock_env : (n <= 98304 ? 64 : 128);
-            if (tblock == 64) {
+            // Default: 64-thread CTAs, 8 per SM (128 registers, 16 warps per SM) — the sweep of DESIGN.md §6; NAV3D_TPE_BLOCK=128
+            // selects the 128-thread kernels (NAV3D_MINB 3: 168 registers / 12 warps, 4: 128 / 16)
+            static const int tblock = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 64;
+            if (tblock == 64 && staged) {
                 cfg.gridDim = dim3((unsigned)((n + 63) / 64)); cfg.blockDim = dim3(64);
-                cudaLaunchKernelEx(&cfg, step_tpe144_kernel, e->P, io);
+                cudaLaunchKernelEx(&cfg, step_tpe_kernel<64, 8, true>, e->P, io);
                 return NAV3D_OK;
             }
             switch (minb * 2 + (staged ? 1 : 0)) {
@@ -1050,10 +1097,9 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         if (G == 1) {
-            static const int tblock_env = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 0;
-            const int tblock = tblock_env ? tblock_env : (e->cfg.n_envs <= 98304 ? 64 : 128);
+            static const int tblock = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 64;
             if (tblock == 64)
-                rollout_tpe144_kernel<<<(unsigned)((e->cfg.n_envs + 63) / 64), 64, 0, s>>>(e->P, T, t0, obs, obs_last,
+                rollout_tpe_kernel<64, 8, true><<<(unsigned)((e->cfg.n_envs + 63) / 64), 64, 0, s>>>(e->P, T, t0, obs, obs_last,
                                                                                                   reward, done, actions_out);
             else if (e->minb == 4)
                 rollout_tpe_kernel<128, 4, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward,
