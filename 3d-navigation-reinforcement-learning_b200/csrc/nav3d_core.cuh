@@ -565,23 +565,14 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
     const bool pon[4] = {wxh, wxl, wyh, wyl};
     const uint32_t pidx[4] = {k_xpart(R, r.x1 + kPadLo) + xbase, k_xpart(R, r.x0 + kPadLo) + xbase,
                               k_ypart(R, r.y1 + kPadLo) + ybase, k_ypart(R, r.y0 + kPadLo) + ybase};
-    const bool queued = STAGED && mq != nullptr;               // the warp marks (coop_marks): only queue the tiles here
+    constexpr bool queued = STAGED;                            // the warp marks (coop_marks): only queue the tiles here (mq != NULL)
+    // (queued) reserve the list slots now; the slots are written further down, once the centre column's loads are issued as
+    // well: the shared-memory atomic's latency would otherwise stall this warp's issue right here
+    int q_at = 0, q_n = 0;
 #ifdef __CUDA_ARCH__
     if (queued && mark) {
-        const int nx = xt1 - xt0 + 1, ny = yt1 - yt0 + 1;        // >= 0 each
-        const int np = (int)wxh + (int)wxl + (int)wyh + (int)wyl;
-        const int n = nx + ny + np;
-        if (n > 0) {
-            int at = atomicAdd(mq->count, n);
-            const uint32_t tag = ((uint32_t)mq->lane << 16) | ((uint32_t)(z - 6 * zbz) << 25);
-            for (int T = xt0; T <= xt1; T++)
-                mq->tasks[at++] = (xbase + (uint32_t)T * xmul) | tag | (tile_mask(xrm, T) << 21);
-            for (int T = yt0; T <= yt1; T++)
-                mq->tasks[at++] = (ybase + (uint32_t)T * ymul) | tag | (tile_mask(yrm, T) << 21) | (1u << 28);
-#pragma unroll
-            for (int d = 0; d < 4; d++)
-                if (pon[d]) mq->tasks[at++] = pidx[d] | tag | (1u << 21) | (1u << 29);
-        }
+        q_n = (xt1 - xt0 + 1) + (yt1 - yt0 + 1) + (int)wxh + (int)wxl + (int)wyh + (int)wyl;
+        if (q_n > 0) q_at = atomicAdd(mq->count, q_n);
     }
 #endif
     if (!queued) tiles_load(xt0, yt0);
@@ -599,6 +590,19 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
 #pragma unroll
         for (int b = 0; b < 3; b++) if (b < nzb) cw_old[b] = cw[b] = K[cbase + ((uint32_t)b << 4)];
     }
+#ifdef __CUDA_ARCH__
+    if (queued && q_n > 0) {
+        int at = q_at;
+        const uint32_t tag = ((uint32_t)mq->lane << 16) | ((uint32_t)(z - 6 * zbz) << 25);
+        for (int T = xt0; T <= xt1; T++)
+            mq->tasks[at++] = (xbase + (uint32_t)T * xmul) | tag | (tile_mask(xrm, T) << 21);
+        for (int T = yt0; T <= yt1; T++)
+            mq->tasks[at++] = (ybase + (uint32_t)T * ymul) | tag | (tile_mask(yrm, T) << 21) | (1u << 28);
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+            if (pon[d]) mq->tasks[at++] = pidx[d] | tag | (1u << 21) | (1u << 29);
+    }
+#endif
 
     // ---- 2. stores to K
     if (owner) {
