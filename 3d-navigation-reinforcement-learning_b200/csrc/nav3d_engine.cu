@@ -624,6 +624,8 @@ struct nav3d_engine {
     int minb = 0;               // __launch_bounds__ min CTAs/SM variant of the step kernel (tuning knob)
     bool simple = false;        // NAV3D_ENV_SIMPLE
     int simple_stride = 0;      // simpleEnv, lanes_per_env == 1: floats per staged row (odd: conflict-free), 0 = not staged
+    bool tpe_staged = true;     // thread-per-env kernels: rows staged in shared memory, marking by the warp (NAV3D_TPE_STAGED)
+    int tpe_block = 64;         // their CTA size (NAV3D_TPE_BLOCK)
     bool reset_seen = false;    // a nav3d_reset call has been made since the rooms were loaded
     bool pdl = true;            // programmatic dependent launch of the step kernel (NAV3D_PDL=0 switches it off)
     float *d_dist_lut = nullptr;
@@ -724,6 +726,8 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     e->minb = (cfg->env_kind == NAV3D_ENV_SIMPLE || G > 1) ? 8 : 3;
     if (const char *mb = getenv("NAV3D_MINB")) { if (atoi(mb) > 0) e->minb = atoi(mb); }   // tuning knob (tools/*sweep.sh)
     if (const char *pd = getenv("NAV3D_PDL")) e->pdl = atoi(pd) != 0;
+    if (const char *v = getenv("NAV3D_TPE_STAGED")) e->tpe_staged = atoi(v) != 0;
+    if (const char *v = getenv("NAV3D_TPE_BLOCK")) e->tpe_block = atoi(v) == 128 ? 128 : 64;
     const size_t N = (size_t)cfg->n_envs;
     cudaError_t err = cudaSuccess;
     if ((err = cudaMalloc(&e->d_states, N * sizeof(EnvState))) != cudaSuccess ||
@@ -745,7 +749,7 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     e->simple = cfg->env_kind == NAV3D_ENV_SIMPLE;
     if (e->simple && G == 1 && simple_dim <= 95) {
         e->simple_stride = simple_dim | 1;
-        if (getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) == 0) e->simple_stride = 0;
+        if (!e->tpe_staged) e->simple_stride = 0;
         else cudaFuncSetAttribute(simple_step_tpe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(kBlock * e->simple_stride * sizeof(float)));
     }
@@ -996,10 +1000,10 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
             return NAV3D_OK;
         }
         if (G == 1) {                                  // thread per env: staged, coalesced observation stores
-            static const bool staged = !(getenv("NAV3D_TPE_STAGED") && atoi(getenv("NAV3D_TPE_STAGED")) == 0);
+            const bool staged = e->tpe_staged;
             // Default: 64-thread CTAs, 8 per SM (128 registers, 16 warps per SM) — the sweep of DESIGN.md §6; NAV3D_TPE_BLOCK=128
             // selects the 128-thread kernels (NAV3D_MINB 3: 168 registers / 12 warps, 4: 128 / 16)
-            static const int tblock = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 64;
+            const int tblock = e->tpe_block;
             if (tblock == 64 && staged) {
                 cfg.gridDim = dim3((unsigned)((n + 63) / 64)); cfg.blockDim = dim3(64);
                 cudaLaunchKernelEx(&cfg, step_tpe_kernel<64, 8, true>, e->P, io);
@@ -1097,7 +1101,7 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
     int rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         if (G == 1) {
-            static const int tblock = getenv("NAV3D_TPE_BLOCK") ? atoi(getenv("NAV3D_TPE_BLOCK")) : 64;
+            const int tblock = e->tpe_block;
             if (tblock == 64)
                 rollout_tpe_kernel<64, 8, true><<<(unsigned)((e->cfg.n_envs + 63) / 64), 64, 0, s>>>(e->P, T, t0, obs, obs_last,
                                                                                                   reward, done, actions_out);

@@ -269,13 +269,16 @@ def test_config3_full_size_sample_against_oracle(oracle):
     assert torch.allclose(obs[:, 72], st[:, 4].float() / free.float(), rtol=0, atol=1e-7)
 
 
-@pytest.mark.parametrize("lanes,minb,staged", [(1, "3", "1"), (1, "3", "0"), (1, "4", "1"), (1, "4", "0"), (4, "6", "1"), (4, "8", "1")])
-def test_kernel_variants(oracle, monkeypatch, lanes, minb, staged):
+@pytest.mark.parametrize("lanes,minb,staged,block", [(1, "0", "1", "64"), (1, "3", "1", "128"), (1, "3", "0", "128"), (1, "4", "1", "128"),
+                                                     (1, "4", "0", "128"), (4, "6", "1", "64"), (4, "8", "1", "64")])
+def test_kernel_variants(oracle, monkeypatch, lanes, minb, staged, block):
     """The instantiations of the step kernel behind the tuning knobs — register budget (__launch_bounds__ min CTAs per SM,
-    NAV3D_MINB), staged or direct observation stores of the thread-per-env kernel (NAV3D_TPE_STAGED), lanes per env — must
+    NAV3D_MINB), CTA size (NAV3D_TPE_BLOCK), staged or direct observation stores of the thread-per-env kernel
+    (NAV3D_TPE_STAGED), lanes per env — must
     give the same bits, auto-reset (an out-of-line device call at the end of the step) included."""
     monkeypatch.setenv("NAV3D_MINB", minb)
     monkeypatch.setenv("NAV3D_TPE_STAGED", staged)
+    monkeypatch.setenv("NAV3D_TPE_BLOCK", block)
     rooms = [load_room_file(ROOMS / "P3_training" / "maze_3d_tunnels.txt"), load_room_file(ROOMS / "P2_training" / "tightcorridor.txt"),
              load_room_file(ROOMS / "P1_training" / "Empty_room_3mx3mx3m_0.25m_cellsize.txt")]
     n_done = lockstep(oracle, rooms, n=1500, L=10, steps=650, seed=21, lanes=lanes, state_every=50)
