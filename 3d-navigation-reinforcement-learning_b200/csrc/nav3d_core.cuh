@@ -113,6 +113,7 @@ struct EngineParams {
     RewardParams rw;
     const float *dist_lut;         // simpleEnv: round(count * cell_size, 2) as f32, count = 0..L (simpleEnv.py:337)
     int32_t obs_dim;               // 80 (CubicEnv) or 6L+7 (simpleEnv)
+    int32_t mark_cap;              // entries of a warp's marking list (32 x mark_tasks_per_lane of the loaded room set)
 };
 
 struct StepIO {                    // per-launch output pointers (any may be null except obs)
@@ -410,11 +411,14 @@ NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &s
 // in a shared-memory list of the warp, and after the step all 32 lanes work the list off evenly (coop_marks in
 // nav3d_engine.cu).  No two tasks of a step touch the same word, so their order does not matter.
 struct MarkQueue {
-    uint32_t *tasks;               // the warp's list (kMarkQueueCap entries)
+    uint32_t *tasks;               // the warp's list (EngineParams::mark_cap entries)
     int *count;                    // its length
     int lane;                      // this thread's lane (the flush finds the env's block through it)
 };
-constexpr int kMarkQueueCap = 32 * 40;      // per lane at most 2 x 17 tiles (rooms are at most 64 cells wide + border) + 4 wall ends
+// Worst case per lane: an x run and a y run of min(2L+1, room width / depth) cells = (len + 6) / 4 tiles each, + 4 wall ends.
+NAV3D_HD int mark_tasks_per_lane(int L, int max_w, int max_d) {
+    return (imin(2 * L + 1, max_w) + 6) / 4 + (imin(2 * L + 1, max_d) + 6) / 4 + 4;
+}
 
 // A code-0 field at bit `sh` of w becomes `code`; returns the new word.
 NAV3D_HD uint32_t mark_field(uint32_t w, int sh, uint32_t code) { return ((w >> sh) & 31u) ? w : (w | (code << sh)); }

@@ -227,10 +227,15 @@ __device__ __forceinline__ void flush_rows(const float *stage_f, float *const *d
 struct WarpWork {
     float stage[32 * kStageStride];
     float *dst[32];
-    uint32_t tasks[kMarkQueueCap];
+    uint32_t *tasks;               // this warp's slice of the CTA's dynamic shared memory (P.mark_cap entries)
     uint32_t env_of_lane[32];
     int n_tasks;
 };
+// dynamic shared memory of a thread-per-env CTA: one marking list per warp
+__device__ __forceinline__ uint32_t *warp_tasks(const EngineParams &P) {
+    extern __shared__ uint32_t dyn_tasks[];
+    return dyn_tasks + (threadIdx.x >> 5) * P.mark_cap;
+}
 
 // Step 1 of get_obs (CubicEnv.py:264-266) for the x / y rays of every env of the warp that is on a first visit: the lanes
 // share the queued tiles evenly.  A task is up to four words of one tile (x run: words tile + 4j, y run: tile + j, a wall
@@ -315,7 +320,7 @@ __device__ __forceinline__ void step_tpe_body(const EngineParams &P, const StepI
     const long long env = io.env0 + gid;
     if (STAGED) {
         w->dst[lane] = nullptr; w->env_of_lane[lane] = (uint32_t)env;
-        if (lane == 0) w->n_tasks = 0;
+        if (lane == 0) { w->n_tasks = 0; w->tasks = warp_tasks(P); }
         __syncwarp();
     }
     bool rst = false;
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(kBlock) reset_tpe_kernel(const __grid_constant
         }
     }
     w->env_of_lane[lane] = mine ? (uint32_t)env : 0u;
-    if (lane == 0) w->n_tasks = 0;
+    if (lane == 0) { w->n_tasks = 0; w->tasks = warp_tasks(P); }
     __syncwarp();
     tpe_reset<true>(P, mine, (uint32_t)env, episode, picks != nullptr, room, k, lut, obs, w, lane);
 }
@@ -381,7 +386,7 @@ __device__ __forceinline__ void rollout_tpe_body(const EngineParams &P, int T, u
     const long long env = gid;
     if (STAGED) {
         w->env_of_lane[lane] = (uint32_t)env;
-        if (lane == 0) w->n_tasks = 0;
+        if (lane == 0) { w->n_tasks = 0; w->tasks = warp_tasks(P); }
         __syncwarp();
     }
     const MarkQueue mq{w->tasks, &w->n_tasks, lane};
@@ -792,6 +797,7 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     std::vector<uint32_t> dense_off((size_t)n_rooms);
     std::vector<int32_t> wall((size_t)n_rooms);
     size_t n_dense = 0, n_occz = 0, n_occ64 = 0, n_free_cap = 0, max_k = 0, max_cells = 0;
+    int max_w = 1, max_d = 1;
     std::vector<uint32_t> start((size_t)n_rooms, 0xffffffffu);
     for (int i = 0; i < n_rooms; i++) {
         const nav3d_room_desc &d = rooms[i];
@@ -819,6 +825,7 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
         wall[(size_t)i] = d.wall_code;
         max_k = std::max(max_k, (size_t)(e->simple ? k2_bytes(R) : k_bytes(R)));
         max_cells = std::max(max_cells, (size_t)d.width * d.depth * d.height);
+        max_w = std::max(max_w, (int)d.width); max_d = std::max(max_d, (int)d.depth);
         // "Start position=" of the room file (CubicEnv.py:415-416, :461-466): used instead of a random start when it is a
         // cell of the room and not a wall (the reference re-picks a random one otherwise)
         if (d.has_start && d.start_x >= 0 && d.start_x < d.width && d.start_y >= 0 && d.start_y < d.depth && d.start_z >= 0 &&
@@ -834,6 +841,7 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     free_rooms(e);
     int8_t *d_dense = nullptr; uint32_t *d_off = nullptr, *d_nwall = nullptr; int32_t *d_wall = nullptr;
     // per-env block: [K bricks of the largest room | overflow bytes (one per cell, touched only by counters >= 29)]
+    e->P.mark_cap = 32 * mark_tasks_per_lane(e->cfg.local_map_length, max_w, max_d);
     size_t ovf_off = align_up(max_k, 128), stride = ovf_off + align_up(max_cells, 128);
     if (e->simple) { ovf_off = 0; stride = align_up(max_k, 128); }
     const size_t know_bytes = stride * (size_t)e->cfg.n_envs;
@@ -959,7 +967,8 @@ int nav3d_reset(nav3d_engine *e, const int32_t *env_ids, int32_t n, const int32_
     e->reset_seen = true;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = NAV3D_OK;
-    if (!e->simple && e->G == 1) reset_tpe_kernel<<<grid_for(n, 1), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
+    if (!e->simple && e->G == 1)
+        reset_tpe_kernel<<<grid_for(n, 1), kBlock, (kBlock / 32) * e->P.mark_cap * sizeof(uint32_t), s>>>(e->P, env_ids, n, picks, obs);
     else rc = dispatch_lanes(e->G, [&](auto g) {
         constexpr int G = decltype(g)::value;
         if (e->simple) simple_reset_kernel<G><<<grid_for(n, G), kBlock, 0, s>>>(e->P, env_ids, n, picks, obs);
@@ -1004,6 +1013,7 @@ int launch_step(nav3d_engine *e, StepIO io, int env0, int n, cudaStream_t s) {
             // Default: 64-thread CTAs, 8 per SM (128 registers, 16 warps per SM) — the sweep of DESIGN.md §6; NAV3D_TPE_BLOCK=128
             // selects the 128-thread kernels (NAV3D_MINB 3: 168 registers / 12 warps, 4: 128 / 16)
             const int tblock = e->tpe_block;
+            cfg.dynamicSmemBytes = (size_t)(tblock / 32) * e->P.mark_cap * sizeof(uint32_t);   // one marking list per warp
             if (tblock == 64 && staged) {
                 cfg.gridDim = dim3((unsigned)((n + 63) / 64)); cfg.blockDim = dim3(64);
                 cudaLaunchKernelEx(&cfg, step_tpe_kernel<64, 8, true>, e->P, io);
@@ -1103,13 +1113,13 @@ int nav3d_rollout_random(nav3d_engine *e, int32_t T, uint32_t t0, float *obs, fl
         if (G == 1) {
             const int tblock = e->tpe_block;
             if (tblock == 64)
-                rollout_tpe_kernel<64, 8, true><<<(unsigned)((e->cfg.n_envs + 63) / 64), 64, 0, s>>>(e->P, T, t0, obs, obs_last,
+                rollout_tpe_kernel<64, 8, true><<<(unsigned)((e->cfg.n_envs + 63) / 64), 64, 2 * e->P.mark_cap * sizeof(uint32_t), s>>>(e->P, T, t0, obs, obs_last,
                                                                                                   reward, done, actions_out);
             else if (e->minb == 4)
-                rollout_tpe_kernel<128, 4, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward,
+                rollout_tpe_kernel<128, 4, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 4 * e->P.mark_cap * sizeof(uint32_t), s>>>(e->P, T, t0, obs, obs_last, reward,
                                                                                             done, actions_out);
             else
-                rollout_tpe_kernel<128, 3, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 0, s>>>(e->P, T, t0, obs, obs_last, reward,
+                rollout_tpe_kernel<128, 3, true><<<grid_for(e->cfg.n_envs, 1), kBlock, 4 * e->P.mark_cap * sizeof(uint32_t), s>>>(e->P, T, t0, obs, obs_last, reward,
                                                                                             done, actions_out);
             return NAV3D_OK;
         }
