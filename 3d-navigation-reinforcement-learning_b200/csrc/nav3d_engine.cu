@@ -842,6 +842,17 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     int8_t *d_dense = nullptr; uint32_t *d_off = nullptr, *d_nwall = nullptr; int32_t *d_wall = nullptr;
     // per-env block: [K bricks of the largest room | overflow bytes (one per cell, touched only by counters >= 29)]
     e->P.mark_cap = 32 * mark_tasks_per_lane(e->cfg.local_map_length, max_w, max_d);
+    if (!e->simple) {
+        // The default thread-per-env kernels: ask for no more shared memory than their 8 CTAs per SM need, so that the rest
+        // of the 256 KB stays L1 (experiment knob NAV3D_CARVEOUT = percent of the maximum shared memory; 0 = driver's choice)
+        const size_t per_cta = 7680 + 2 * e->P.mark_cap * sizeof(uint32_t) + 1024;
+        int pct = (int)((8 * per_cta * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (const char *v = getenv("NAV3D_CARVEOUT")) pct = atoi(v);
+        if (pct > 0 && pct <= 100) {
+            cudaFuncSetAttribute(step_tpe_kernel<64, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(rollout_tpe_kernel<64, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+    }
     size_t ovf_off = align_up(max_k, 128), stride = ovf_off + align_up(max_cells, 128);
     if (e->simple) { ovf_off = 0; stride = align_up(max_k, 128); }
     const size_t know_bytes = stride * (size_t)e->cfg.n_envs;

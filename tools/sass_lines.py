@@ -34,7 +34,8 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(out.splitlines()))
 h = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
 hdr = rows[h]
-ia, iaddr, isamp = hdr.index("Instructions Executed"), hdr.index("Address"), hdr.index("# Samples")
+# NAV3D_COL: sum another per-instruction column of the source page instead (e.g. "L2 Theoretical Sectors Global")
+ia, iaddr, isamp = hdr.index(os.environ.get("NAV3D_COL", "Instructions Executed")), hdr.index("Address"), hdr.index("# Samples")
 data = [r for r in rows[h + 1:] if len(r) > ia and r[ia].isdigit()]
 base = int(data[0][iaddr], 16)
 per_line, samples, total, missing = defaultdict(int), defaultdict(int), 0, 0
