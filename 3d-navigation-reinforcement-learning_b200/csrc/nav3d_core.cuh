@@ -406,14 +406,16 @@ NAV3D_HD void write_scalars(const EngineParams &P, int lane, const ObsScalars &s
 
 // Ray marking by the WARP (thread-per-env kernels).  With one thread per env a warp executes the union of its 32 envs'
 // paths: marking in the thread costs every lane the longest run of the warp.  Instead a thread on a first visit only
-// QUEUES its marking tiles — one u32 per tile: word index of the tile in the env's block (16 bits) | lane (5) << 16 | cell
-// mask (4) << 21 | z field (3) << 25 | y-run (words tile + j instead of tile + 4j) << 28 | wall code instead of seen << 29 —
-// in a shared-memory list of the warp, and after the step all 32 lanes work the list off evenly (coop_marks in
-// nav3d_engine.cu).  No two tasks of a step touch the same word, so their order does not matter.
+// QUEUES its marking tiles — one u32 per tile: word index of the tile in the env's block (16 bits) | lane (5) << 16 | tile
+// number along the run (5) << 21 | z field (3) << 26 | y run (words tile + j instead of tile + 4j) << 29 | a single wall-end
+// word << 30 — in a shared-memory list of the warp, with the free range and the centre coordinate of its two runs in
+// `desc`, and after the step all 32 lanes work the list off evenly (coop_marks in nav3d_engine.cu), each deriving the cell
+// mask of its tile from the run's description.  No two tasks of a step touch the same word: their order does not matter.
 struct MarkQueue {
     uint32_t *tasks;               // the warp's list (EngineParams::mark_cap entries)
     int *count;                    // its length
-    int lane;                      // this thread's lane (the flush finds the env's block through it)
+    uint32_t *desc;                // [2][32]: per lane the x run and the y run as first | last << 8 | centre << 16
+    int lane;                      // this thread's lane (the flush finds the env's block and the runs through it)
 };
 // Worst case per lane: an x run and a y run of min(2L+1, room width / depth) cells = (len + 6) / 4 tiles each, + 4 wall ends.
 NAV3D_HD int mark_tasks_per_lane(int L, int max_w, int max_d) {
@@ -597,14 +599,14 @@ NAV3D_HD uint32_t observe(const EngineParams &P, const RoomDev &R, uint8_t *envk
 #ifdef __CUDA_ARCH__
     if (queued && q_n > 0) {
         int at = q_at;
-        const uint32_t tag = ((uint32_t)mq->lane << 16) | ((uint32_t)(z - 6 * zbz) << 25);
-        for (int T = xt0; T <= xt1; T++)
-            mq->tasks[at++] = (xbase + (uint32_t)T * xmul) | tag | (tile_mask(xrm, T) << 21);
-        for (int T = yt0; T <= yt1; T++)
-            mq->tasks[at++] = (ybase + (uint32_t)T * ymul) | tag | (tile_mask(yrm, T) << 21) | (1u << 28);
+        const uint32_t tag = ((uint32_t)mq->lane << 16) | ((uint32_t)(z - 6 * zbz) << 26);
+        mq->desc[mq->lane] = (uint32_t)(fx0 & 255) | ((uint32_t)(fx1 & 255) << 8) | ((uint32_t)x << 16);
+        mq->desc[32 + mq->lane] = (uint32_t)(fy0 & 255) | ((uint32_t)(fy1 & 255) << 8) | ((uint32_t)y << 16);
+        for (int T = xt0; T <= xt1; T++) mq->tasks[at++] = (xbase + (uint32_t)T * xmul) | tag | ((uint32_t)T << 21);
+        for (int T = yt0; T <= yt1; T++) mq->tasks[at++] = (ybase + (uint32_t)T * ymul) | tag | ((uint32_t)T << 21) | (1u << 29);
 #pragma unroll
         for (int d = 0; d < 4; d++)
-            if (pon[d]) mq->tasks[at++] = pidx[d] | tag | (1u << 21) | (1u << 29);
+            if (pon[d]) mq->tasks[at++] = pidx[d] | tag | (1u << 30);
     }
 #endif
 

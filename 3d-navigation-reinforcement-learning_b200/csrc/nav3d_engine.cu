@@ -229,6 +229,7 @@ struct WarpWork {
     float *dst[32];
     uint32_t *tasks;               // this warp's slice of the CTA's dynamic shared memory (P.mark_cap entries)
     uint32_t env_of_lane[32];
+    uint32_t desc[64];             // MarkQueue::desc
     int n_tasks;
 };
 // dynamic shared memory of a thread-per-env CTA: one marking list per warp
@@ -253,19 +254,28 @@ __device__ __forceinline__ void coop_marks(const EngineParams &P, WarpWork *w, i
 #pragma unroll
         for (int c = 0; c < CH; c++) {
             const int i = i0 + c * 32 + lane;
-            const uint32_t t = i < total ? w->tasks[i] : 0u;     // 0: empty mask
+            const uint32_t t = i < total ? w->tasks[i] : 0u;      // (no task: empty mask below, z field 0)
+            const uint32_t tl = (t >> 16) & 31u, yrun = (t >> 29) & 1u;
             meta[c] = t;
-            Kp[c] = reinterpret_cast<uint32_t *>(P.know + (unsigned long long)w->env_of_lane[(t >> 16) & 31u] * P.env_stride) +
-                    (t & 0xffffu);
-            const uint32_t m = (t >> 21) & 15u, stride = (t & (1u << 28)) ? 1u : 4u;
+            Kp[c] = reinterpret_cast<uint32_t *>(P.know + (unsigned long long)w->env_of_lane[tl] * P.env_stride) + (t & 0xffffu);
+            // the tile's cells 4T - pad + j that lie in the run's free range and are not its centre
+            const uint32_t d = w->desc[yrun * 32u + tl];
+            const int c0 = 4 * (int)((t >> 21) & 31u) - kPadLo;
+            const int lo_ = min(max((int)(d & 255u) - c0, 0), 4), up = min(max(c0 + 3 - (int)((d >> 8) & 255u), 0), 4);
+            uint32_t m = (0xfu << lo_) & (0xfu >> up) & 0xfu;
+            const int sk = (int)((d >> 16) & 255u) - c0;
+            if (sk >= 0 && sk <= 3) m &= ~(1u << sk);
+            if (t & (1u << 30)) m = 1u;                            // a wall end: the one word the task names
+            if (i >= total) m = 0u;
+            const uint32_t stride = yrun ? 1u : 4u;
 #pragma unroll
             for (int j = 0; j < 4; j++) v[c][j] = ((m >> j) & 1u) ? Kp[c][j * stride] : 0xffffffffu;
         }
         if (first) { between(); first = false; }
 #pragma unroll
         for (int c = 0; c < CH; c++) {
-            const uint32_t t = meta[c], zsh = 5u * ((t >> 25) & 7u), stride = (t & (1u << 28)) ? 1u : 4u;
-            const uint32_t code = ((t & (1u << 29)) ? kCodeWall : kCodeSeen) << zsh;
+            const uint32_t t = meta[c], zsh = 5u * ((t >> 26) & 7u), stride = (t & (1u << 29)) ? 1u : 4u;
+            const uint32_t code = ((t & (1u << 30)) ? kCodeWall : kCodeSeen) << zsh;
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (((v[c][j] >> zsh) & 31u) == 0u) Kp[c][j * stride] = v[c][j] | code;
@@ -297,7 +307,7 @@ __device__ __noinline__ void tpe_reset(const EngineParams &P, bool mine, uint32_
     if (mine) {
         ResetCtx c;
         float *row = obs ? obs + (unsigned long long)env * kObsDim : nullptr;
-        MarkQueue mq{w->tasks, &w->n_tasks, lane};
+        MarkQueue mq{w->tasks, &w->n_tasks, w->desc, lane};
         if (STAGED) { w->dst[lane] = row; if (row) row = w->stage + lane * kStageStride; }
         const uint32_t nbr = reset_lane<1, STAGED>(P, (int)env, 0, room, k, episode + 1u, lut, row, c, STAGED ? &mq : nullptr);
         reset_commit(P, (int)env, 0, c, nbr);
@@ -325,7 +335,7 @@ __device__ __forceinline__ void step_tpe_body(const EngineParams &P, const StepI
     }
     bool rst = false;
     if (valid) {
-        MarkQueue mq{w->tasks, &w->n_tasks, lane};
+        MarkQueue mq{w->tasks, &w->n_tasks, w->desc, lane};
         rst = step_env<1, false, STAGED>(P, io, (int)env, 0, lane, (int)io.actions[env], lut, env, nullptr, nullptr,
                                          w->stage + lane * kStageStride, w->dst + lane, STAGED ? &mq : nullptr);
     }
@@ -389,7 +399,7 @@ __device__ __forceinline__ void rollout_tpe_body(const EngineParams &P, int T, u
         if (lane == 0) { w->n_tasks = 0; w->tasks = warp_tasks(P); }
         __syncwarp();
     }
-    const MarkQueue mq{w->tasks, &w->n_tasks, lane};
+    const MarkQueue mq{w->tasks, &w->n_tasks, w->desc, lane};
     EnvState st;
     if (valid) st = P.states[env];
     for (int t = 0; t < T; t++) {
