@@ -185,15 +185,16 @@ __global__ void __launch_bounds__(kBlock, MINB) step_call_kernel(const __grid_co
 // zero padding.  Two passes so that every store instruction runs ONE code path: the 16 window float4 of two envs per
 // instruction (lane l: column l % 16 of env 2i + l / 16: 2 x 256 contiguous bytes), then the 4 scalar float4 of eight envs
 // per instruction (lane l: quad 16 + l % 4 of env 8i + l / 4: 8 x 64 contiguous bytes).
-__device__ __forceinline__ void flush_rows(const float *stage_f, float *const *dst, int lane, const float *lut, int L) {
-    const uint32_t *stage = reinterpret_cast<const uint32_t *>(stage_f);
-    __syncwarp();
+// CONTIG: the 32 rows are consecutive rows of one array starting at d0 (the usual case: no env of the warp finished, none is
+// past the range) — no destination look-up, no test per store.
+template <bool CONTIG>
+__device__ __forceinline__ void flush_rows_t(const uint32_t *stage, float *const *dst, float *d0, int lane, const float *lut, int L) {
     const int j = lane & 15, eh = lane >> 4;
 #pragma unroll 4
     for (int i = 0; i < 16; i++) {
         const int e = 2 * i + eh;
-        float *d = dst[e];
-        if (d == nullptr) continue;                                // (a row that was not staged holds stale words)
+        float *d = CONTIG ? d0 + e * kObsDim : dst[e];
+        if (!CONTIG && d == nullptr) continue;                     // (a row that was not staged holds stale words)
         const uint32_t q = stage[e * kStageStride + j];
         float4 v;
         v.x = lut[q & 31u]; v.y = lut[(q >> 5) & 31u]; v.z = lut[(q >> 10) & 31u]; v.w = lut[q >> 15];
@@ -203,8 +204,8 @@ __device__ __forceinline__ void flush_rows(const float *stage_f, float *const *d
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int e = 8 * i + e4;
-        float *d = dst[e];
-        if (d == nullptr) continue;
+        float *d = CONTIG ? d0 + e * kObsDim : dst[e];
+        if (!CONTIG && d == nullptr) continue;
         const uint32_t sc = stage[e * kStageStride + kStageScalars], down = sc >> 8;
         const float ex = __uint_as_float(stage[e * kStageStride + kStageExplored]);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -219,6 +220,14 @@ __device__ __forceinline__ void flush_rows(const float *stage_f, float *const *d
         } else if (k == 2) v.x = ex;                               // visited / total (:291); quad 19 is padding
         __stcs(reinterpret_cast<float4 *>(d) + 16 + k, v);
     }
+}
+__device__ __forceinline__ void flush_rows(const float *stage_f, float *const *dst, int lane, const float *lut, int L) {
+    const uint32_t *stage = reinterpret_cast<const uint32_t *>(stage_f);
+    __syncwarp();
+    float *d0 = dst[0];
+    const bool contig = __all_sync(0xffffffffu, d0 != nullptr && dst[lane] == d0 + lane * kObsDim);
+    if (contig) flush_rows_t<true>(stage, dst, d0, lane, lut, L);
+    else flush_rows_t<false>(stage, dst, d0, lane, lut, L);
     __syncwarp();
 }
 
