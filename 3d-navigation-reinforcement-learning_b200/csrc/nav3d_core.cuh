@@ -21,9 +21,14 @@
 //     knows where it moves, whether that is a first visit and what the new counter is BEFORE it loads anything; every
 //     load of the step (window columns, ray marking) is therefore issued in one batch.
 //   Observations clip counters at 20 and the reward at 25 (CubicEnv.py:273-274, :180); counters saturate at 255.
-// Within a step every word of K has at most one writing lane, and a lane that reads a word another lane may be marking
-// re-derives the marks from the ray extents in registers, so a step needs no intra-group barrier; the only cross-lane
-// traffic is one OR-reduction of the neighbour codes.
+// Within a step every word of K has at most one writer, and whoever reads a word that is being marked in the same step
+// re-derives the marks from the ray extents in registers, so the window gather never waits for the marking stores.
+// Two mappings of envs to threads share this source:
+//   * G = 1 with STAGED (the default kernels of nav3d_engine.cu): one thread owns an env; its observation row leaves in
+//     compact form through a shared-memory staging tile that the warp expands and writes out, and its ray marking is
+//     queued for the warp (MarkQueue) instead of being done in the thread;
+//   * G = 2 .. 32 lanes per env (and G = 1 without STAGED): the lanes split the window columns and the marking tiles, each
+//     lane streams its own float4s; the only cross-lane traffic is one OR-reduction of the neighbour codes.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
