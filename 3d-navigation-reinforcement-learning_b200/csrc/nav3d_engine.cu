@@ -520,13 +520,22 @@ __global__ void __launch_bounds__(kBlock) simple_reset_kernel(EngineParams P, co
 // caller's [N, 6L+7] array — with coalesced 128-byte store instructions.  Dynamic shared memory: kBlock x stride floats.
 __device__ __forceinline__ void flush_rows_n(const float *stage, int stride, float *const *dst, int obs_dim, int lane) {
     __syncwarp();
-    int e = 0, j = lane;
-    while (j >= obs_dim) { j -= obs_dim; e++; }
-    while (e < 32) {
-        float *d = dst[e];
-        if (d != nullptr) __stcs(d + j, stage[e * stride + j]);
-        j += 32;
+    float *d0 = dst[0];
+    if (stride == obs_dim && __all_sync(0xffffffffu, d0 != nullptr && dst[lane] == d0 + lane * obs_dim)) {
+        // the usual case: 32 consecutive rows of one array, staged back to back (6L+7 is odd: conflict-free as it is) —
+        // one linear copy of 32 x (6L+7) floats, 128 bytes per store instruction
+        const int n = 32 * obs_dim;
+#pragma unroll 4
+        for (int i = lane; i < n; i += 32) __stcs(d0 + i, stage[i]);
+    } else {
+        int e = 0, j = lane;
         while (j >= obs_dim) { j -= obs_dim; e++; }
+        while (e < 32) {
+            float *d = dst[e];
+            if (d != nullptr) __stcs(d + j, stage[e * stride + j]);
+            j += 32;
+            while (j >= obs_dim) { j -= obs_dim; e++; }
+        }
     }
     __syncwarp();
 }
@@ -772,7 +781,7 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
     P.rw = reference_reward_params(cfg->crash_penalty);
     e->simple = cfg->env_kind == NAV3D_ENV_SIMPLE;
     if (e->simple && G == 1 && simple_dim <= 95) {
-        e->simple_stride = simple_dim | 1;
+        e->simple_stride = simple_dim;          // 6L+7 is odd: 32 rows at this stride fall into 32 different banks
         if (!e->tpe_staged) e->simple_stride = 0;
         else cudaFuncSetAttribute(simple_step_tpe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(kBlock * e->simple_stride * sizeof(float)));
