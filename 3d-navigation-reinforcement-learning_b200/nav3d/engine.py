@@ -152,7 +152,7 @@ class Engine:
             if episodes is not None:
                 self._check(episodes, torch.int32, (N, 8), "episodes")
             args = tuple(_ptr(t) for t in tensors)
-            if len(self._step_args) >= 256:
+            if len(self._step_args) >= 16384:        # (a rollout with one action row per step cycles through thousands of keys)
                 self._step_args.clear()
             self._step_args[key] = args
         check(self._lib.nav3d_step(self._h, *args, self._stream()))
