@@ -742,8 +742,8 @@ int nav3d_create(const nav3d_config *cfg, nav3d_engine **out) {
         return fail(NAV3D_ERR_INVALID, "env_kind must be NAV3D_ENV_CUBIC or NAV3D_ENV_SIMPLE");
     if (cfg->local_map_length < 1 || cfg->local_map_length > 255)
         return fail(NAV3D_ERR_UNSUPPORTED, "local_map_length must be in 1..255");
-    // Defaults from the sweeps in DESIGN.md §6: CubicEnv one thread per env (the step_tpe / rollout_tpe kernels, 3 CTAs of
-    // 128 threads per SM with every register the step wants); simpleEnv (6L ray cells, no window) 2 lanes per env.
+    // Defaults from the sweeps in DESIGN.md §6: one thread per env — CubicEnv: the step_tpe / rollout_tpe kernels, 8 CTAs of
+    // 64 threads per SM at 128 registers; simpleEnv: simple_step_tpe_kernel (rows of more than 95 floats: 2 lanes per env).
     const int simple_dim = 6 * cfg->local_map_length + 7;
     int G = cfg->lanes_per_env == 0 ? ((cfg->env_kind == NAV3D_ENV_SIMPLE && simple_dim > 95) ? 2 : 1) : cfg->lanes_per_env;
     if (!(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32))
