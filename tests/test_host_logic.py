@@ -71,3 +71,19 @@ def test_spaces():
     assert a.n == 6 and o.shape == (80,) and o.dtype == np.float32
     a, o = simple_spaces(4)
     assert o.shape == (31,)
+
+
+def test_marking_list_capacity_bound():
+    """csrc/nav3d_core.cuh mark_tasks_per_lane: a warp's shared-memory marking list holds 32 x [(min(2L+1, W) + 6) / 4 +
+    (min(2L+1, D) + 6) / 4 + 4] tasks.  Brute force over every agent position: an x (y) run of the cells within L of the
+    agent never spans more tiles of the bordered volume (2 border columns, 4 columns per tile) than the bound allows."""
+    def bound(L, w):
+        return (min(2 * L + 1, w) + 6) // 4
+
+    for L in list(range(1, 34)) + [40, 100, 255]:
+        for w in range(3, 65):
+            worst = 0
+            for x in range(w):
+                f0, f1 = max(0, x - L), min(w - 1, x + L)
+                worst = max(worst, ((f1 + 2) >> 2) - ((f0 + 2) >> 2) + 1)
+            assert worst <= bound(L, w), (L, w, worst)
