@@ -870,6 +870,8 @@ int nav3d_load_rooms(nav3d_engine *e, int32_t n_rooms, const nav3d_room_desc *ro
     int8_t *d_dense = nullptr; uint32_t *d_off = nullptr, *d_nwall = nullptr; int32_t *d_wall = nullptr;
     // per-env block: [K bricks of the largest room | overflow bytes (one per cell, touched only by counters >= 29)]
     e->P.mark_cap = 32 * mark_tasks_per_lane(e->cfg.local_map_length, max_w, max_d);
+    if (!e->simple && max_k / 4 > 65536)          // a marking task names its tile by a 16-bit word index (MarkQueue)
+        return fail(NAV3D_ERR_UNSUPPORTED, "room too large for the marking-task encoding (K volume above 65 536 words)");
     if (!e->simple) {
         // The default thread-per-env kernels: ask for no more shared memory than their 8 CTAs per SM need, so that the rest
         // of the 256 KB stays L1 (experiment knob NAV3D_CARVEOUT = percent of the maximum shared memory; 0 = driver's choice)
